@@ -1,0 +1,654 @@
+// cuberille_capi.cu — the C-ABI of include/cuberille_c.h: handle, buffers, kernel launches.
+//
+// Host-side orchestration of GenerateData() (txx:59-216) as a two-phase run:
+//   cub_count : K1 classify -> K2 count + decoupled look-back scan      (sizes are data dependent)
+//   cub_emit  : K3 emit points + cells -> [K4 project] -> [K5 split projected quads]
+// Everything is ordered on one CUDA stream.  There is no CPU implementation behind this file.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/cuberille_c.h"
+#include "cub_common.cuh"
+#include "k_classify.cuh"
+#include "k_count_scan.cuh"
+#include "k_emit.cuh"
+#include "k_generate.cuh"
+#include "k_project.cuh"
+
+using namespace cub;
+
+namespace {
+
+constexpr int kEmitTX = 6;   // words (x32 voxels) per CTA column
+constexpr int kEmitTY = 14;  // rows per CTA column  -> (6+2)*(14+2) = 128 threads
+constexpr int kNumSMs = 148;
+
+template <typename P>
+struct DevBuf {
+  P* p = nullptr;
+  size_t cap = 0;  // elements
+};
+
+}  // namespace
+
+struct cub_handle_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::string err = "";
+
+  // volume
+  const void* d_vol = nullptr;
+  DevBuf<unsigned char> vol_owned;
+  int dtype = -1, pix_bytes = 0;
+  uint64_t dims[3] = {0, 0, 0};
+  Geom geom{};
+  bool has_volume = false;
+  // slab
+  uint64_t image_nz = 0, local_z0 = 0, own_z0 = 0, own_z1 = 0;
+
+  // scratch
+  DevBuf<uint32_t> bits, vofs, fofs;
+  uint64_t bits_layout[3] = {0, 0, 0};
+  DevBuf<unsigned long long> status;  // 2 * n_tiles
+  unsigned int* d_ticket = nullptr;
+  unsigned long long* d_totals = nullptr;  // 6
+  unsigned long long* h_totals = nullptr;  // pinned, 6
+
+  // results
+  DevBuf<float> points;
+  DevBuf<unsigned char> cells, celldata;
+  DevBuf<uint4> quads;
+
+  // state
+  cub_params params{};
+  Grid g{};
+  bool counted = false, emitted = false;
+  int zs0 = 0, zs1 = 0, owner_z_min = 0;
+  uint64_t n_points = 0, n_quads = 0, n_cells = 0, ghost_v = 0, ghost_f = 0;
+  uint64_t point_base = 0, cell_base = 0;
+  int id_bytes = 4, verts_per_cell = 4;
+  double step_used = 0.0;
+
+  bool timing = false;
+  cudaEvent_t ev[10] = {};
+  float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t launches = 0;
+};
+
+namespace {
+
+int fail(cub_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf;
+  return code;
+}
+
+#define CU_TRY(h, call)                                                                              \
+  do {                                                                                               \
+    cudaError_t e__ = (call);                                                                        \
+    if (e__ != cudaSuccess)                                                                          \
+      return fail(h, e__ == cudaErrorMemoryAllocation ? CUB_ERR_NOMEM : CUB_ERR_CUDA, "%s: %s (%s:%d)", #call, \
+                  cudaGetErrorString(e__), __FILE__, __LINE__);                                      \
+  } while (0)
+
+#define CUB_TRY(call)              \
+  do {                             \
+    int rc__ = (call);             \
+    if (rc__ != CUB_OK) return rc__; \
+  } while (0)
+
+template <typename P>
+int ensure(cub_handle h, DevBuf<P>& b, size_t n, bool zero_on_alloc = false) {
+  if (n <= b.cap && b.p) return CUB_OK;
+  if (b.p) {
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+    CU_TRY(h, cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+  }
+  if (n == 0) n = 1;
+  void* p = nullptr;
+  CU_TRY(h, cudaMalloc(&p, n * sizeof(P)));
+  b.p = static_cast<P*>(p);
+  b.cap = n;
+  if (zero_on_alloc) CU_TRY(h, cudaMemsetAsync(p, 0, n * sizeof(P), h->stream));
+  return CUB_OK;
+}
+
+int pixel_bytes(int dtype) {
+  switch (dtype) {
+    case CUB_U8: case CUB_I8: return 1;
+    case CUB_U16: case CUB_I16: return 2;
+    case CUB_U32: case CUB_I32: case CUB_F32: return 4;
+    case CUB_F64: return 8;
+    default: return 0;
+  }
+}
+
+#define DISPATCH_PIXEL(dtype, CALL)                          \
+  switch (dtype) {                                           \
+    case CUB_U8:  { typedef unsigned char  T; CALL; } break; \
+    case CUB_I8:  { typedef signed char    T; CALL; } break; \
+    case CUB_U16: { typedef unsigned short T; CALL; } break; \
+    case CUB_I16: { typedef short          T; CALL; } break; \
+    case CUB_U32: { typedef unsigned int   T; CALL; } break; \
+    case CUB_I32: { typedef int            T; CALL; } break; \
+    case CUB_F32: { typedef float          T; CALL; } break; \
+    case CUB_F64: { typedef double         T; CALL; } break; \
+    default: break;                                          \
+  }
+
+// (double)(T)iso : m_IsoSurfaceValue is an InputPixelType (h:326)
+double iso_as_pixel(int dtype, double iso) {
+  double r = iso;
+  DISPATCH_PIXEL(dtype, r = (double)(T)iso);
+  return r;
+}
+
+struct Timer {
+  cub_handle h;
+  int slot;
+  Timer(cub_handle h_, int slot_) : h(h_), slot(slot_) {
+    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+  }
+  void stop() {
+    if (h->timing) {
+      cudaEventRecord(h->ev[1], h->stream);
+      cudaEventSynchronize(h->ev[1]);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]);
+      h->ms[slot] = ms;
+    }
+  }
+};
+
+template <typename T>
+void launch_classify(cub_handle h) {
+  const Grid& g = h->g;
+  const int groups = (g.Wx + kWordsPerTask - 1) / kWordsPerTask;
+  const long long rows = (long long)g.Y * g.Zl;
+  const long long tasks = rows * groups;
+  long long blocks = (tasks + 7) / 8;
+  const long long max_blocks = (long long)kNumSMs * 16;
+  if (blocks > max_blocks) blocks = max_blocks;
+  if (blocks < 1) blocks = 1;
+  k_classify<T><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
+                                                         (T)h->params.iso_value, tasks, groups);
+  h->launches++;
+}
+
+int launch_project(cub_handle h, float* pts, size_t n) {
+  if (n == 0) return CUB_OK;
+  ProjArgs a;
+  a.vol = h->d_vol;
+  a.g = h->g;
+  a.geom = h->geom;
+  a.iso = iso_as_pixel(h->dtype, h->params.iso_value);
+  a.thr = h->params.surface_distance_threshold;
+  a.step0 = h->step_used;
+  a.relax = h->params.step_relaxation;
+  a.max_steps = h->params.max_steps;
+  a.points = pts;
+  a.n_points = n;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  DISPATCH_PIXEL(h->dtype, (k_project<T><<<blocks, 128, 0, h->stream>>>(a)));
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  return CUB_OK;
+}
+
+// geometry of the run: Grid + own range in local coordinates
+int setup_grid(cub_handle h) {
+  if (!h->has_volume) return fail(h, CUB_ERR_INVALID, "no volume set");
+  Grid& g = h->g;
+  g.X = (int)h->dims[0];
+  g.Y = (int)h->dims[1];
+  g.Zl = (int)h->dims[2];
+  g.Wx = (g.X + 31) / 32;
+  g.Wp = (g.Wx + 3) & ~3;
+  g.zg0 = (int)h->local_z0;
+  g.Zg = (int)h->image_nz;
+  h->zs0 = (int)(h->own_z0 - h->local_z0);
+  h->zs1 = (int)(h->own_z1 - h->local_z0);
+  h->owner_z_min = (h->own_z0 > 0) ? h->zs0 - 1 : h->zs0;
+  return CUB_OK;
+}
+
+void compute_step(cub_handle h) {
+  // txx:75-85: auto step length = max spacing * 0.25
+  double ms = h->geom.spacing[0];
+  for (int a = 1; a < 3; ++a) ms = h->geom.spacing[a] > ms ? h->geom.spacing[a] : ms;
+  h->step_used = h->params.step_length < 0.0 ? ms * 0.25 : h->params.step_length;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cub_abi_version(void) { return CUB_ABI_VERSION; }
+
+void cub_default_params(cub_params* p) {
+  if (!p) return;
+  memset(p, 0, sizeof *p);
+  p->iso_value = 1.0;  // NumericTraits<InputPixelType>::One  (txx:34)
+  p->generate_triangles = 1;
+  p->project_vertices = 1;
+  p->save_pixel_as_cell_data = 0;
+  p->surface_distance_threshold = 0.5;
+  p->step_length = -1.0;
+  p->step_relaxation = 0.95;
+  p->max_steps = 50;
+}
+
+int cub_create(int device, void* stream, cub_handle* out) {
+  if (!out) return CUB_ERR_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return CUB_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return CUB_ERR_CUDA;
+  cub_handle h = new (std::nothrow) cub_handle_s;
+  if (!h) return CUB_ERR_NOMEM;
+  h->device = device;
+  if (stream) {
+    h->stream = static_cast<cudaStream_t>(stream);
+  } else {
+    if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return CUB_ERR_CUDA; }
+    h->own_stream = true;
+  }
+  bool ok = cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
+            cudaMalloc(&h->d_totals, 6 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost(&h->h_totals, 6 * sizeof(unsigned long long)) == cudaSuccess;
+  for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+  if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
+  cub_default_params(&h->params);
+  *out = h;
+  return CUB_OK;
+}
+
+int cub_destroy(cub_handle h) {
+  if (!h) return CUB_OK;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  cudaFree(h->vol_owned.p);
+  cudaFree(h->bits.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
+  cudaFree(h->d_ticket); cudaFree(h->d_totals);
+  if (h->h_totals) cudaFreeHost(h->h_totals);
+  cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
+  for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  if (h->own_stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return CUB_OK;
+}
+
+const char* cub_last_error(cub_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+static int set_geometry(cub_handle h, int dtype, const uint64_t dims[3], const double spacing[3],
+                        const double origin[3], const double direction[9]) {
+  if (!dims) return fail(h, CUB_ERR_INVALID, "dims is null");
+  const int pb = pixel_bytes(dtype);
+  if (!pb) return fail(h, CUB_ERR_INVALID, "unknown dtype %d", dtype);
+  for (int a = 0; a < 3; ++a)
+    if (dims[a] == 0 || dims[a] >= (1ull << 31)) return fail(h, CUB_ERR_INVALID, "dims[%d]=%llu out of range", a, (unsigned long long)dims[a]);
+  if (direction) {
+    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int i = 0; i < 9; ++i)
+      if (direction[i] != I[i]) return fail(h, CUB_ERR_UNSUPPORTED, "only the identity direction matrix is supported");
+  }
+  for (int a = 0; a < 3; ++a) {
+    const double s = spacing ? spacing[a] : 1.0;
+    if (!(s > 0.0) || !std::isfinite(s)) return fail(h, CUB_ERR_INVALID, "spacing[%d] must be positive and finite", a);
+    h->geom.spacing[a] = s;
+    h->geom.origin[a] = origin ? origin[a] : 0.0;
+    h->dims[a] = dims[a];
+  }
+  h->dtype = dtype;
+  h->pix_bytes = pb;
+  h->image_nz = dims[2];
+  h->local_z0 = 0;
+  h->own_z0 = 0;
+  h->own_z1 = dims[2];
+  h->counted = h->emitted = false;
+  return CUB_OK;
+}
+
+int cub_set_volume(cub_handle h, const void* data, int dtype, const uint64_t dims[3], const double spacing[3],
+                   const double origin[3], const double direction[9], int mem_kind) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!data) return fail(h, CUB_ERR_INVALID, "data is null");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->has_volume = false;
+  CUB_TRY(set_geometry(h, dtype, dims, spacing, origin, direction));
+  const size_t bytes = (size_t)dims[0] * dims[1] * dims[2] * h->pix_bytes;
+  if (mem_kind == CUB_MEM_DEVICE) {
+    h->d_vol = data;
+  } else if (mem_kind == CUB_MEM_HOST) {
+    CUB_TRY(ensure(h, h->vol_owned, bytes));
+    CU_TRY(h, cudaMemcpyAsync(h->vol_owned.p, data, bytes, cudaMemcpyHostToDevice, h->stream));
+    h->d_vol = h->vol_owned.p;
+  } else {
+    return fail(h, CUB_ERR_INVALID, "bad mem_kind %d", mem_kind);
+  }
+  h->has_volume = true;
+  return CUB_OK;
+}
+
+int cub_set_slab(cub_handle h, uint64_t image_nz, uint64_t local_z0, uint64_t own_z0, uint64_t own_z1) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->has_volume) return fail(h, CUB_ERR_INVALID, "cub_set_slab before cub_set_volume");
+  const uint64_t zl = h->dims[2];
+  if (image_nz == 0 || image_nz >= (1ull << 31) || local_z0 + zl > image_nz)
+    return fail(h, CUB_ERR_INVALID, "local buffer [%llu,%llu) exceeds image_nz %llu", (unsigned long long)local_z0,
+                (unsigned long long)(local_z0 + zl), (unsigned long long)image_nz);
+  if (!(own_z0 < own_z1) || own_z1 > image_nz) return fail(h, CUB_ERR_INVALID, "bad own range");
+  const uint64_t need_lo = own_z0 >= 2 ? own_z0 - 2 : 0;
+  const uint64_t need_hi = own_z1 + 1 < image_nz ? own_z1 + 1 : image_nz;
+  if (local_z0 > need_lo || local_z0 + zl < need_hi)
+    return fail(h, CUB_ERR_INVALID, "local buffer must cover slices [%llu,%llu) (own range plus halo)",
+                (unsigned long long)need_lo, (unsigned long long)need_hi);
+  h->image_nz = image_nz;
+  h->local_z0 = local_z0;
+  h->own_z0 = own_z0;
+  h->own_z1 = own_z1;
+  h->counted = h->emitted = false;
+  return CUB_OK;
+}
+
+int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n_quads) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!p) return fail(h, CUB_ERR_INVALID, "params is null");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->counted = h->emitted = false;
+  h->params = *p;
+  CUB_TRY(setup_grid(h));
+  if (iso_as_pixel(h->dtype, p->iso_value) != p->iso_value)
+    return fail(h, CUB_ERR_INVALID, "iso value %.17g is not representable in the pixel type", p->iso_value);
+  compute_step(h);
+  const Grid& g = h->g;
+  const size_t words = (size_t)g.Zl * g.Y * g.Wp;
+  const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
+                              h->bits_layout[2] != (uint64_t)g.Zl;
+  const bool had = h->bits.p && h->bits.cap >= words;
+  CUB_TRY(ensure(h, h->bits, words));
+  CUB_TRY(ensure(h, h->vofs, words));
+  CUB_TRY(ensure(h, h->fofs, words));
+  if ((!had || layout_changed) && g.Wp != g.Wx) CU_TRY(h, cudaMemsetAsync(h->bits.p, 0, words * 4, h->stream));
+  h->bits_layout[0] = g.X; h->bits_layout[1] = g.Y; h->bits_layout[2] = g.Zl;
+
+  if (h->timing) cudaEventRecord(h->ev[2], h->stream);
+
+  // K1
+  {
+    Timer t(h, 0);
+    DISPATCH_PIXEL(h->dtype, launch_classify<T>(h));
+    CU_TRY(h, cudaGetLastError());
+    t.stop();
+  }
+  // K2
+  const size_t word_begin = (size_t)h->owner_z_min * g.Y * g.Wp;
+  const size_t n_words = (size_t)(h->zs1 - h->owner_z_min) * g.Y * g.Wp;
+  const size_t n_tiles = (n_words + kScanTileWords - 1) / kScanTileWords;
+  CUB_TRY(ensure(h, h->status, 2 * n_tiles));
+  {
+    Timer t(h, 1);
+    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 2 * n_tiles * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    ScanState st{h->status.p, h->status.p + n_tiles, h->d_ticket, h->d_totals};
+    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(h->bits.p, h->vofs.p, h->fofs.p, g, word_begin,
+                                                                    n_words, st);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * g.Y * g.Wp : (size_t)-1;
+    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, mark0, (size_t)-1, h->d_totals);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    t.stop();
+  }
+  CU_TRY(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (h->timing) {
+    cudaEventRecord(h->ev[3], h->stream);
+    cudaEventSynchronize(h->ev[3]);
+    cudaEventElapsedTime(&h->ms[5], h->ev[2], h->ev[3]);
+  }
+  const uint64_t tot_v = h->h_totals[0], tot_f = h->h_totals[1];
+  if (tot_v >= (1ull << 32) || tot_f >= (1ull << 32))
+    return fail(h, CUB_ERR_OVERFLOW, "more than 2^32 vertices or faces in one handle (%llu, %llu): split into z-slabs",
+                (unsigned long long)tot_v, (unsigned long long)tot_f);
+  h->ghost_v = h->h_totals[2];
+  h->ghost_f = h->h_totals[3];
+  h->n_points = tot_v - h->ghost_v;
+  h->n_quads = tot_f - h->ghost_f;
+  h->point_base = h->cell_base = 0;
+  h->counted = true;
+  if (n_points) *n_points = h->n_points;
+  if (n_quads) *n_quads = h->n_quads;
+  return CUB_OK;
+}
+
+int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base) {
+  if (!h) return CUB_ERR_INVALID;
+  h->point_base = point_id_base;
+  h->cell_base = cell_id_base;
+  return CUB_OK;
+}
+
+int cub_emit(cub_handle h, int id_bytes) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_emit before cub_count");
+  if (id_bytes != 4 && id_bytes != 8) return fail(h, CUB_ERR_INVALID, "id_bytes must be 4 or 8");
+  CU_TRY(h, cudaSetDevice(h->device));
+  const cub_params& P = h->params;
+  const Grid& g = h->g;
+  const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0, cd = P.save_pixel_as_cell_data != 0;
+  const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
+  h->verts_per_cell = tri ? 3 : 4;
+  h->n_cells = tri ? 2 * h->n_quads : h->n_quads;
+  h->id_bytes = id_bytes;
+  if (id_bytes == 4 && h->point_base + h->n_points > (1ull << 32))
+    return fail(h, CUB_ERR_OVERFLOW, "point ids up to %llu do not fit 32 bits", (unsigned long long)(h->point_base + h->n_points));
+
+  const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
+  CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
+  CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
+  if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
+  if (cd) CUB_TRY(ensure(h, h->celldata, (size_t)h->n_cells * h->pix_bytes));
+
+  if (h->timing) cudaEventRecord(h->ev[4], h->stream);
+  const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
+  if (h->n_quads > 0) {
+    Timer t(h, 2);
+    EmitArgs a;
+    a.bits = h->bits.p; a.vofs = h->vofs.p; a.fofs = h->fofs.p;
+    a.g = g; a.geom = h->geom;
+    a.zs0 = h->zs0; a.zs1 = h->zs1; a.owner_z_min = h->owner_z_min;
+    const int gx = (g.Wx + kEmitTX - 1) / kEmitTX, gy = (g.Y + kEmitTY - 1) / kEmitTY;
+    const int nz = h->zs1 - h->zs0;
+    int tz = 32;
+    while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 4LL * kNumSMs) tz >>= 1;
+    if (tz > nz) tz = nz;
+    a.tz = tz;
+    a.ghost_f = (uint32_t)h->ghost_f;
+    a.id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
+    a.points = h->points.p;
+    a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
+    a.mode = mode;
+    a.emit_ghost_points = ghost_points ? 1 : 0;
+    a.vol = cd ? h->d_vol : nullptr;
+    a.celldata = cd ? h->celldata.p : nullptr;
+    a.pix_bytes = h->pix_bytes;
+    dim3 grid(gx, gy, (nz + tz - 1) / tz);
+    constexpr int threads = (kEmitTX + 2) * (kEmitTY + 2);
+    if (id_bytes == 4) k_emit<kEmitTX, kEmitTY, uint32_t><<<grid, threads, 0, h->stream>>>(a);
+    else k_emit<kEmitTX, kEmitTY, unsigned long long><<<grid, threads, 0, h->stream>>>(a);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    t.stop();
+  }
+  if (proj && h->n_points > 0) {
+    Timer t(h, 3);
+    const size_t start = ghost_points ? 0 : (size_t)h->ghost_v;
+    CUB_TRY(launch_project(h, h->points.p + 3 * start, n_pts_all - start));
+    t.stop();
+  }
+  if (mode == kEmitScratchQuads && h->n_quads > 0) {
+    Timer t(h, 4);
+    const unsigned blocks = (unsigned)((h->n_quads + 255) / 256);
+    const unsigned long long delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
+    if (id_bytes == 4)
+      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, (size_t)h->n_quads, delta);
+    else
+      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, (size_t)h->n_quads, delta);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    t.stop();
+  }
+  if (h->timing) {
+    cudaEventRecord(h->ev[5], h->stream);
+    cudaEventSynchronize(h->ev[5]);
+    cudaEventElapsedTime(&h->ms[6], h->ev[4], h->ev[5]);
+  }
+  h->emitted = true;
+  return CUB_OK;
+}
+
+int cub_run(cub_handle h, const cub_params* p, int id_bytes, uint64_t* n_points, uint64_t* n_cells) {
+  uint64_t np = 0, nq = 0;
+  CUB_TRY(cub_count(h, p, &np, &nq));
+  CUB_TRY(cub_emit(h, id_bytes));
+  if (n_points) *n_points = h->n_points;
+  if (n_cells) *n_cells = h->n_cells;
+  return CUB_OK;
+}
+
+int cub_fetch(cub_handle h, float* points, void* cells, void* cell_data, int mem_kind) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->emitted) return fail(h, CUB_ERR_INVALID, "cub_fetch before cub_emit");
+  CU_TRY(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind k = mem_kind == CUB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+  if (points && h->n_points)
+    CU_TRY(h, cudaMemcpyAsync(points, h->points.p + 3 * (size_t)h->ghost_v, (size_t)h->n_points * 12, k, h->stream));
+  if (cells && h->n_cells)
+    CU_TRY(h, cudaMemcpyAsync(cells, h->cells.p, (size_t)h->n_cells * h->verts_per_cell * h->id_bytes, k, h->stream));
+  if (cell_data && h->n_cells) {
+    if (!h->params.save_pixel_as_cell_data) return fail(h, CUB_ERR_INVALID, "cell data was not requested");
+    CU_TRY(h, cudaMemcpyAsync(cell_data, h->celldata.p, (size_t)h->n_cells * h->pix_bytes, k, h->stream));
+  }
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CUB_OK;
+}
+
+int cub_device_buffers(cub_handle h, const float** points, const void** cells, const void** cell_data,
+                       uint64_t* n_points, uint64_t* n_cells, int* verts_per_cell, int* id_bytes) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->emitted) return fail(h, CUB_ERR_INVALID, "no mesh has been emitted");
+  if (points) *points = h->points.p + 3 * (size_t)h->ghost_v;
+  if (cells) *cells = h->cells.p;
+  if (cell_data) *cell_data = h->params.save_pixel_as_cell_data ? h->celldata.p : nullptr;
+  if (n_points) *n_points = h->n_points;
+  if (n_cells) *n_cells = h->n_cells;
+  if (verts_per_cell) *verts_per_cell = h->verts_per_cell;
+  if (id_bytes) *id_bytes = h->id_bytes;
+  return CUB_OK;
+}
+
+int cub_debug_bitmask(cub_handle h, uint32_t* out, uint64_t* words_per_row) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_debug_bitmask before cub_count");
+  if (words_per_row) *words_per_row = (uint64_t)h->g.Wp;
+  if (out) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    const size_t words = (size_t)h->g.Zl * h->g.Y * h->g.Wp;
+    CU_TRY(h, cudaMemcpyAsync(out, h->bits.p, words * 4, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(h, cudaStreamSynchronize(h->stream));
+  }
+  return CUB_OK;
+}
+
+int cub_debug_project_points(cub_handle h, const cub_params* p, float* points_xyz, uint64_t n_points) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!p || !points_xyz) return fail(h, CUB_ERR_INVALID, "null argument");
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->params = *p;
+  CUB_TRY(setup_grid(h));
+  compute_step(h);
+  h->counted = h->emitted = false;
+  CUB_TRY(ensure(h, h->points, 3 * (size_t)n_points));
+  CU_TRY(h, cudaMemcpyAsync(h->points.p, points_xyz, (size_t)n_points * 12, cudaMemcpyHostToDevice, h->stream));
+  CUB_TRY(launch_project(h, h->points.p, (size_t)n_points));
+  CU_TRY(h, cudaMemcpyAsync(points_xyz, h->points.p, (size_t)n_points * 12, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CUB_OK;
+}
+
+int cub_generate_volume(cub_handle h, int kind, const uint64_t dims[3], const uint64_t image_dims[3], uint64_t z_offset,
+                        double param0, double param1, uint64_t seed) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!dims || !image_dims) return fail(h, CUB_ERR_INVALID, "null dims");
+  if (kind < 0 || kind > 2) return fail(h, CUB_ERR_INVALID, "unknown generator %d", kind);
+  CU_TRY(h, cudaSetDevice(h->device));
+  h->has_volume = false;
+  CUB_TRY(set_geometry(h, CUB_F32, dims, nullptr, nullptr, nullptr));
+  if (z_offset + dims[2] > image_dims[2] || dims[0] != image_dims[0] || dims[1] != image_dims[1])
+    return fail(h, CUB_ERR_INVALID, "slab does not fit the image");
+  const size_t n = (size_t)dims[0] * dims[1] * dims[2];
+  CUB_TRY(ensure(h, h->vol_owned, n * 4));
+  GenArgs a;
+  a.out = reinterpret_cast<float*>(h->vol_owned.p);
+  a.X = (int)dims[0]; a.Y = (int)dims[1]; a.Zl = (int)dims[2];
+  a.IX = (int)image_dims[0]; a.IY = (int)image_dims[1]; a.IZ = (int)image_dims[2];
+  a.zg0 = (int)z_offset;
+  a.kind = kind;
+  a.p0 = (float)param0; a.p1 = (float)param1;
+  a.seed = seed;
+  size_t blocks = (n + 255) / 256;
+  if (blocks > (size_t)kNumSMs * 32) blocks = (size_t)kNumSMs * 32;
+  k_generate<<<(unsigned)blocks, 256, 0, h->stream>>>(a);
+  h->launches++;
+  CU_TRY(h, cudaGetLastError());
+  h->d_vol = h->vol_owned.p;
+  h->has_volume = true;
+  h->image_nz = image_dims[2];
+  h->local_z0 = z_offset;
+  // own range defaults to the whole local buffer; callers with halos follow up with cub_set_slab
+  h->own_z0 = z_offset;
+  h->own_z1 = z_offset + dims[2];
+  return CUB_OK;
+}
+
+int cub_download_volume(cub_handle h, void* out, uint64_t bytes) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->has_volume || !out) return fail(h, CUB_ERR_INVALID, "no volume / null buffer");
+  const uint64_t have = h->dims[0] * h->dims[1] * h->dims[2] * (uint64_t)h->pix_bytes;
+  if (bytes != have) return fail(h, CUB_ERR_INVALID, "size mismatch: volume has %llu bytes", (unsigned long long)have);
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMemcpyAsync(out, h->d_vol, bytes, cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CUB_OK;
+}
+
+int cub_enable_timing(cub_handle h, int on) {
+  if (!h) return CUB_ERR_INVALID;
+  h->timing = on != 0;
+  return CUB_OK;
+}
+
+int cub_get_timings(cub_handle h, float ms[8]) {
+  if (!h || !ms) return CUB_ERR_INVALID;
+  for (int i = 0; i < 8; ++i) ms[i] = h->ms[i];
+  return CUB_OK;
+}
+
+uint64_t cub_launch_count(cub_handle h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,229 @@
+"""GPU: the CUDA path, called through the C-ABI, against the CPU oracle on the same inputs.
+Bar: bit-exact connectivity, vertex count, vertex order and positions (projected ones included:
+the kernel reproduces the oracle's arithmetic, which is tighter than the 1e-5 x spacing of the spec)."""
+import numpy as np
+import pytest
+
+from util import KAT, KAT_ARGS, assert_mesh_equal, gyroid, oracle, pkg, random_volume, read_fixture, run_filter, smooth_volume
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("row", KAT, ids=[r[0] for r in KAT])
+def test_reference_known_answers_on_gpu(row):
+    """the reference's 19 CTest rows (Testing/CMakeLists.txt:10-331) through the filter interface"""
+    name, fixture, iso, exp_points, exp_cells, tri, proj, max_steps = row
+    img = read_fixture(fixture)
+    mesh = run_filter(img, iso, triangles=tri, project=proj, max_steps=max_steps, **KAT_ARGS)
+    assert mesh.GetNumberOfPoints() == exp_points
+    assert mesh.GetNumberOfCells() == exp_cells
+    ref = oracle().cuberille(img.data, iso, triangles=tri, project=proj, max_steps=max_steps, **KAT_ARGS)
+    assert_mesh_equal(mesh, ref, name)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(7, 9, 33), (5, 6, 1), (3, 1, 70), (1, 8, 8), (6, 5, 32), (4, 4, 31), (9, 13, 131)])
+def test_bitmask_matches_oracle(dtype, shape):
+    """K1: inside == !(v < iso) for every pixel type and ragged row lengths"""
+    P, O = pkg(), oracle()
+    vol, iso = random_volume(shape, dtype, seed=sum(shape))
+    h = P.capi.Handle(0)
+    h.set_volume(vol)
+    p = P.capi.default_params()
+    p.iso_value = float(iso)
+    h.count(p)
+    got = h.bitmask()
+    wpr = got.shape[2]
+    ref = O.classify(vol, iso, wpr)
+    nx = shape[2]
+    valid = np.zeros(wpr * 32, bool)
+    valid[:nx] = True
+    mask = np.packbits(valid.reshape(-1, 32)[:, ::-1], axis=1).view(">u4").astype(np.uint32).reshape(-1)
+    assert np.array_equal(got & mask, ref & mask)
+    # padding bits of the last valid word replicate voxel X-1
+    if nx % 32:
+        w, b = (nx - 1) // 32, (nx - 1) % 32
+        last = (got[:, :, w] >> b) & 1
+        pad = got[:, :, w] >> (b + 1)
+        assert np.array_equal(pad, np.where(last == 1, np.uint32(0xFFFFFFFF) >> (b + 1), 0))
+    h.close()
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.uint16, np.float32, np.float64, np.int32])
+@pytest.mark.parametrize("shape,fill", [((6, 7, 8), 0.5), ((9, 33, 65), 0.5), ((17, 20, 97), 0.2), ((12, 40, 200), 0.8),
+                                        ((2, 3, 4), 0.5), ((1, 1, 1), 0.5), ((3, 3, 1), 0.5), ((1, 5, 40), 0.5)])
+def test_noise_volumes_ids_and_connectivity(dtype, shape, fill):
+    """iid noise exercises every corner configuration of the first-touch rule, with inside voxels on
+    the image border (no faces there); quads and fixed-split triangles, unprojected: exact positions"""
+    O = oracle()
+    vol, iso = random_volume(shape, dtype, seed=shape[2] * 7 + int(fill * 10), fill=fill)
+    for tri in (False, True):
+        ref = O.cuberille(vol, iso, triangles=tri, project=False, mode=O.CLOSED_FORM)
+        mesh = run_filter(vol, iso, triangles=tri, project=False)
+        assert_mesh_equal(mesh, ref, f"{dtype.__name__} {shape} tri={tri}")
+
+
+def test_noise_volume_literal_lookup_agrees_too():
+    O = oracle()
+    vol, iso = random_volume((14, 21, 45), np.uint8, seed=3)
+    assert (vol >= iso).reshape(vol.shape[0], -1).any(axis=1).all()  # no empty slice: the literal loop is well defined
+    ref = O.cuberille(vol, iso, triangles=False, project=False, mode=O.LITERAL)
+    assert_mesh_equal(run_filter(vol, iso, triangles=False, project=False), ref, "literal")
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.float32])
+@pytest.mark.parametrize("tri", [False, True])
+def test_smooth_volumes_with_projection(dtype, tri):
+    """K4 + K5: projection and the projected-diagonal triangle split, bit-exact against the oracle"""
+    O = oracle()
+    vol, iso = smooth_volume((40, 37, 70), dtype, seed=11)
+    vol[0], vol[-1], vol[:, 0], vol[:, -1], vol[:, :, 0], vol[:, :, -1] = 0, 0, 0, 0, 0, 0
+    args = dict(thr=0.05, step=0.3, relax=0.9, max_steps=60)
+    ref = O.cuberille(vol, iso, triangles=tri, project=True, **args)
+    mesh = run_filter(vol, iso, triangles=tri, project=True, **args)
+    assert ref.points.shape[0] > 1000
+    assert_mesh_equal(mesh, ref, f"{dtype.__name__} tri={tri}")
+
+
+def test_anisotropic_spacing_and_origin():
+    O = oracle()
+    vol = gyroid((30, 26, 44), 11.0)
+    sp, og = (0.5, 2.0, 1.25), (-3.0, 10.5, 0.75)
+    for proj in (False, True):
+        ref = O.cuberille(vol, 0.0, triangles=True, project=proj, thr=0.01, spacing=sp, origin=og)
+        mesh = run_filter(vol, 0.0, triangles=True, project=proj, thr=0.01, spacing=sp, origin=og)
+        assert_mesh_equal(mesh, ref, f"spacing proj={proj}")
+
+
+def test_auto_step_length_and_default_parameters():
+    """constructor defaults (txx:31-41) incl. step = max spacing * 0.25 (txx:82-85)"""
+    O, P = oracle(), pkg()
+    img = read_fixture("nucleon")
+    f = P.CuberilleImageToMeshFilter.New()
+    f.SetInput(img)
+    f.SetIsoSurfaceValue(140)
+    f.Update()
+    assert f.GetProjectVertexStepLength() == 0.25  # sticky
+    ref = O.cuberille(img.data, 140)
+    assert ref.step_length_used == 0.25
+    assert_mesh_equal(f.GetOutput(), ref, "defaults")
+
+
+@pytest.mark.parametrize("tri,proj", [(False, False), (True, False), (True, True)])
+def test_save_pixel_as_cell_data(tri, proj):
+    O = oracle()
+    vol, iso = smooth_volume((20, 22, 40), np.int16, seed=5)
+    ref = O.cuberille(vol, iso, triangles=tri, project=proj, cell_data=True)
+    mesh = run_filter(vol, iso, triangles=tri, project=proj, cell_data=True)
+    assert_mesh_equal(mesh, ref, "celldata")
+    assert mesh.cell_data.dtype == np.int16 and (mesh.cell_data >= iso).all()
+
+
+def test_64_bit_ids():
+    O = oracle()
+    vol, iso = random_volume((10, 12, 40), np.uint8, seed=9)
+    ref = O.cuberille(vol, iso, triangles=True, project=True, mode=O.CLOSED_FORM)
+    mesh = run_filter(vol, iso, triangles=True, project=True, id_bytes=8)
+    assert mesh.cells.dtype == np.uint64
+    assert_mesh_equal(mesh, ref, "u64")
+
+
+def test_empty_and_full_volumes():
+    for fillv in (0, 200):
+        vol = np.full((6, 7, 40), fillv, np.uint8)
+        mesh = run_filter(vol, 100, triangles=True, project=True)
+        assert mesh.GetNumberOfPoints() == 0 and mesh.GetNumberOfCells() == 0
+
+
+def test_nan_pixels():
+    O = oracle()
+    vol = np.zeros((6, 6, 36), np.float32)
+    vol[2, 3, 33] = np.nan
+    vol[3, 3, 0] = np.nan  # on the border: no face towards the outside
+    ref = O.cuberille(vol, 0.5, triangles=False, project=False, mode=O.CLOSED_FORM)
+    assert_mesh_equal(run_filter(vol, 0.5, triangles=False, project=False), ref, "nan")
+
+
+@pytest.mark.parametrize("n_slabs", [2, 3, 5])
+@pytest.mark.parametrize("tri,proj", [(False, False), (True, True)])
+def test_z_slabs_concatenate_to_the_single_run(n_slabs, tri, proj):
+    """§8e on one GPU: each slab runs with its halo, ids are offset by the exclusive scan of the slab
+    counts, and the concatenation equals the whole-image mesh (shared boundary vertices belong to the
+    first-touch owner, i.e. the lower slab)"""
+    P, O = pkg(), oracle()
+    vol = gyroid((41, 30, 50), 13.0)
+    ref = O.cuberille(vol, 0.0, triangles=tri, project=proj, thr=0.01)
+    nz = vol.shape[0]
+    bounds = np.linspace(0, nz, n_slabs + 1).astype(int)
+    halo = 9 if proj else 2
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices, p.surface_distance_threshold = 0.0, int(tri), int(proj), 0.01
+    handles, counts = [], []
+    for s in range(n_slabs):
+        z0, z1 = int(bounds[s]), int(bounds[s + 1])
+        lo, hi = max(0, z0 - halo), min(nz, z1 + halo)
+        h = P.capi.Handle(0)
+        h.set_volume(vol[lo:hi])
+        h.set_slab(nz, lo, z0, z1)
+        counts.append(h.count(p))
+        handles.append(h)
+    pts, cells, pbase, cbase = [], [], 0, 0
+    for h, (np_, nq) in zip(handles, counts):
+        h.set_id_base(pbase, cbase)
+        h.emit(4)
+        a, b, _ = h.fetch()
+        pts.append(a)
+        cells.append(b)
+        pbase += np_
+        cbase += nq * (2 if tri else 1)
+        h.close()
+    mesh = P.Mesh(np.concatenate(pts), np.concatenate(cells))
+    assert_mesh_equal(mesh, ref, f"{n_slabs} slabs")
+
+
+def test_projection_kernel_alone_on_arbitrary_points():
+    """K4 on points that are not lattice corners, including points outside the image (clamped reads)"""
+    P, O = pkg(), oracle()
+    img = read_fixture("neghip")
+    rng = np.random.default_rng(0)
+    pts = (rng.random((20000, 3)) * (np.array(img.data.shape[::-1]) + 4) - 2).astype(np.float32)
+    h = P.capi.Handle(0)
+    h.set_volume(img.data)
+    p = P.capi.default_params()
+    p.iso_value, p.surface_distance_threshold, p.step_length, p.max_steps = 55.0, 0.2, 0.24, 100
+    got = h.project_points(p, pts)
+    ref = O.project_points(img.data, 55, pts, thr=0.2, step=0.24, relax=0.95, max_steps=100)
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    h.close()
+
+
+def test_device_generated_gyroid_round_trip():
+    """bench input path: generate on the device, download the bytes, feed the SAME bytes to the oracle"""
+    P, O = pkg(), oracle()
+    h = P.capi.Handle(0)
+    h.generate(P.capi.GEN_GYROID, (96, 64, 48), p0=24.0)
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = 0.0, 0, 0
+    n_pts, n_cells = h.run(p)
+    vol = h.download_volume()
+    assert vol.shape == (48, 64, 96) and (vol[0] == -2).all() and (vol[:, :, 0] == -2).all()
+    ref = O.cuberille(vol, 0.0, triangles=False, project=False)
+    a, b, _ = h.fetch()
+    assert_mesh_equal(P.Mesh(a, b), ref, "generated gyroid")
+    assert n_pts == ref.points.shape[0] and n_cells == ref.cells.shape[0]
+    h.close()
+
+
+def test_filter_rerun_with_changed_parameters_and_inputs():
+    """a filter instance is reused across Update() calls (buffers are recycled, results are not stale)"""
+    O, P = oracle(), pkg()
+    f = P.CuberilleImageToMeshFilter.New()
+    for fixture, iso, tri in [("fuel", 15, True), ("neghip", 55, False), ("blob3", 200, True), ("fuel", 40, False)]:
+        img = read_fixture(fixture)
+        f.SetInput(img)
+        f.SetIsoSurfaceValue(iso)
+        f.SetGenerateTriangleFaces(tri)
+        f.SetProjectVertexStepLength(0.24)
+        f.Update()
+        ref = O.cuberille(img.data, iso, triangles=tri, project=True, step=0.24)
+        assert_mesh_equal(f.GetOutput(), ref, fixture)

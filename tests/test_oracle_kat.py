@@ -1,0 +1,123 @@
+"""CPU: the oracle against every known-answer test the reference holds for this path
+(Testing/CMakeLists.txt:10-331; the driver asserts only #points / #cells,
+Testing/CuberilleTest01.cxx:193-204) plus self-consistency of the restatement."""
+import numpy as np
+import pytest
+
+from util import KAT, KAT_ARGS, gyroid, oracle, random_volume, read_fixture
+
+
+@pytest.mark.parametrize("row", KAT, ids=[r[0] for r in KAT])
+def test_reference_known_answers(row):
+    name, fixture, iso, exp_points, exp_cells, tri, proj, max_steps = row
+    O = oracle()
+    img = read_fixture(fixture)
+    assert img.data.dtype == np.uint8 and img.spacing == (1.0, 1.0, 1.0)
+    for mode in (O.LITERAL, O.CLOSED_FORM):
+        m = O.cuberille(img.data, iso, triangles=tri, project=proj, mode=mode, max_steps=max_steps, **KAT_ARGS)
+        assert m.points.shape[0] == exp_points
+        assert m.cells.shape[0] == exp_cells
+        assert np.isfinite(m.points).all()
+
+
+@pytest.mark.parametrize("fixture,iso", [("fuel", 15), ("nucleon", 140), ("blob3", 200)])
+def test_literal_lookup_equals_closed_form(fixture, iso):
+    """the two-plane std::map emulation (txx:155-161,186-191) and the first-touch closed form give
+    the same ids when no interior z-slice is empty"""
+    O = oracle()
+    img = read_fixture(fixture)
+    a = O.cuberille(img.data, iso, triangles=True, project=True, mode=O.LITERAL, max_steps=100, **KAT_ARGS)
+    b = O.cuberille(img.data, iso, triangles=True, project=True, mode=O.CLOSED_FORM, max_steps=100, **KAT_ARGS)
+    assert np.array_equal(a.cells, b.cells)
+    assert np.array_equal(a.points.view(np.uint32), b.points.view(np.uint32))
+
+
+def test_unprojected_quads_are_unit_squares_and_order_is_first_touch():
+    O = oracle()
+    vol = gyroid(24, 12.0)
+    m = O.cuberille(vol, 0.0, triangles=False, project=False)
+    p = m.points[m.cells.astype(np.int64)]  # (n, 4, 3)
+    edges = np.linalg.norm(p - np.roll(p, -1, axis=1), axis=2)
+    assert np.all(edges == 1.0)
+    # every coordinate is index - 0.5 exactly
+    assert np.all((m.points + 0.5) == np.rint(m.points + 0.5))
+    # every id is used, and a vertex is created no later than the voxel that first uses it: the largest id
+    # seen up to any cell never exceeds (distinct ids so far) + 7 (the other corners of that voxel)
+    flat = m.cells.reshape(-1).astype(np.int64)
+    assert np.array_equal(np.unique(flat), np.arange(m.points.shape[0]))
+    first = np.full(m.points.shape[0], flat.size, np.int64)
+    np.minimum.at(first, flat, np.arange(flat.size))
+    order = np.argsort(first, kind="stable")
+    assert np.all(np.abs(order - np.arange(order.size)) <= 7)
+
+
+def test_triangles_are_two_per_quad_and_share_the_quad_vertices():
+    O = oracle()
+    vol = gyroid(20, 10.0)
+    q = O.cuberille(vol, 0.0, triangles=False, project=True, thr=0.01)
+    t = O.cuberille(vol, 0.0, triangles=True, project=True, thr=0.01)
+    assert t.cells.shape[0] == 2 * q.cells.shape[0]
+    assert np.array_equal(q.points.view(np.uint32), t.points.view(np.uint32))
+    tt = t.cells.reshape(-1, 6)
+    for quad, tri in zip(q.cells[:500], tt[:500]):
+        assert set(quad) == set(tri)
+        assert (list(tri) == [quad[0], quad[1], quad[3], quad[1], quad[2], quad[3]]
+                or list(tri) == [quad[0], quad[1], quad[2], quad[0], quad[2], quad[3]])
+
+
+def test_border_voxels_make_no_faces():
+    """ZeroFluxNeumann edge replicate: an inside voxel on the image border has no face there (txx:167, h:55-57)"""
+    O = oracle()
+    vol = np.full((4, 5, 6), 10, np.uint8)  # everything inside
+    m = O.cuberille(vol, 5, triangles=False, project=False)
+    assert m.points.shape[0] == 0 and m.cells.shape[0] == 0
+    vol[1:3, 1:4, 1:5] = 0  # a hole: faces point into it
+    m = O.cuberille(vol, 5, triangles=False, project=False)
+    assert m.cells.shape[0] == 2 * (3 * 4 + 2 * 3 + 2 * 4)
+
+
+def test_empty_slice_quirk_is_reproduced_by_literal_mode_only():
+    """lastZ only advances on inside voxels, so an empty z-slice between two occupied
+    ones makes the literal loop reuse the corner plane: 12 points instead of 16."""
+    O = oracle()
+    vol = np.zeros((10, 5, 5), np.uint8)
+    vol[5, 2, 2] = 9
+    vol[7, 2, 2] = 9
+    a = O.cuberille(vol, 5, triangles=False, project=False, mode=O.LITERAL)
+    b = O.cuberille(vol, 5, triangles=False, project=False, mode=O.CLOSED_FORM)
+    assert a.points.shape[0] == 12 and b.points.shape[0] == 16
+    assert a.cells.shape[0] == 12 and b.cells.shape[0] == 12
+
+
+def test_nan_pixels_count_as_inside():
+    O = oracle()
+    vol = np.zeros((5, 5, 5), np.float32)
+    vol[2, 2, 2] = np.nan  # !(nan < iso) -> inside, never "outside"
+    m = O.cuberille(vol, 0.5, triangles=False, project=False)
+    assert m.cells.shape[0] == 6 and m.points.shape[0] == 8
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64])
+def test_all_pixel_types(dtype):
+    O = oracle()
+    vol, iso = random_volume((9, 10, 11), dtype, 5)
+    a = O.cuberille(vol, iso, triangles=False, project=False, mode=O.LITERAL)
+    b = O.cuberille(vol, iso, triangles=False, project=False, mode=O.CLOSED_FORM)
+    assert a.cells.shape[0] > 0
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.points, b.points)
+    bits = O.classify(vol, iso)
+    inside = ~(vol < np.asarray(iso).astype(vol.dtype))
+    unpacked = ((bits[:, :, :, None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(vol.shape[0], vol.shape[1], -1)
+    assert np.array_equal(unpacked[:, :, : vol.shape[2]].astype(bool), inside)
+
+
+def test_projection_moves_vertices_towards_the_iso_value():
+    O = oracle()
+    img = read_fixture("fuel")
+    m0 = O.cuberille(img.data, 15, triangles=False, project=False)
+    m1 = O.cuberille(img.data, 15, triangles=False, project=True, max_steps=100, **KAT_ARGS)
+    v0, _ = O.sample(img.data, m0.points.astype(np.float64))
+    v1, _ = O.sample(img.data, m1.points.astype(np.float64))
+    assert np.mean(np.abs(v1 - 15) < 0.2) > 0.95
+    assert np.mean(np.abs(v1 - 15)) < np.mean(np.abs(v0 - 15))
+    assert np.max(np.linalg.norm(m1.points - m0.points, axis=1)) < 5.0
