@@ -17,16 +17,17 @@
 #include "cub_common.cuh"
 #include "k_classify.cuh"
 #include "k_count_scan.cuh"
-#include "k_emit.cuh"
 #include "k_generate.cuh"
 #include "k_project.cuh"
+#include "k_sweep.cuh"
 
 using namespace cub;
 
 namespace {
 
-constexpr int kEmitTX = 6;   // words (x32 voxels) per CTA column
-constexpr int kEmitTY = 14;  // rows per CTA column  -> (6+2)*(14+2) = 128 threads
+// thread grids of the sweep kernels (corner words x corner rows per CTA), see k_sweep.cuh
+constexpr int kCountNTX = 16, kCountNTY = 16;  // 15 x 15 voxel words counted per CTA step
+constexpr int kEmitNTX = 16, kEmitNTY = 16;    // 13 x 13 voxel words emitted per CTA step
 constexpr int kNumSMs = 148;
 
 template <typename P>
@@ -54,7 +55,7 @@ struct cub_handle_s {
   uint64_t image_nz = 0, local_z0 = 0, own_z0 = 0, own_z1 = 0;
 
   // scratch
-  DevBuf<uint32_t> bits, vofs, fofs;
+  DevBuf<uint32_t> bits, cnt, vofs, fofs;
   uint64_t bits_layout[3] = {0, 0, 0};
   DevBuf<unsigned long long> status;  // 2 * n_tiles
   unsigned int* d_ticket = nullptr;
@@ -176,15 +177,20 @@ struct Timer {
 template <typename T>
 void launch_classify(cub_handle h) {
   const Grid& g = h->g;
-  const int groups = (g.Wx + kWordsPerTask - 1) / kWordsPerTask;
-  const long long rows = (long long)g.Y * g.Zl;
-  const long long tasks = rows * groups;
-  long long blocks = (tasks + 7) / 8;
-  const long long max_blocks = (long long)kNumSMs * 16;
+  const unsigned groups = (unsigned)((g.Wx + kWordsPerTask - 1) / kWordsPerTask);
+  const unsigned long long rows = (unsigned long long)g.Y * g.Zl;
+  const unsigned tasks = (unsigned)(rows * groups);  // dims < 2^31 and cub_count checks rows*groups < 2^32
+  unsigned long long blocks = ((unsigned long long)tasks + 7) / 8;
+  const unsigned long long max_blocks = (unsigned long long)kNumSMs * 8 * 4;  // 8 resident CTAs/SM, a few waves
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-  k_classify<T><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
-                                                         (T)h->params.iso_value, tasks, groups);
+  const bool full = (g.X % 32 == 0) && (g.Wx % kWordsPerTask == 0);
+  if (full)
+    k_classify<T, true><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
+                                                                 (T)h->params.iso_value, tasks, groups);
+  else
+    k_classify<T, false><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
+                                                                  (T)h->params.iso_value, tasks, groups);
   h->launches++;
 }
 
@@ -223,6 +229,14 @@ int setup_grid(cub_handle h) {
   h->zs1 = (int)(h->own_z1 - h->local_z0);
   h->owner_z_min = (h->own_z0 > 0) ? h->zs0 - 1 : h->zs0;
   return CUB_OK;
+}
+
+// slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
+int pick_tz(int gx, int gy, int nz) {
+  int tz = 32;
+  while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * kNumSMs) tz >>= 1;
+  if (tz > nz) tz = nz;
+  return tz < 1 ? 1 : tz;
 }
 
 void compute_step(cub_handle h) {
@@ -281,7 +295,7 @@ int cub_destroy(cub_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
-  cudaFree(h->bits.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
+  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
   cudaFree(h->d_ticket); cudaFree(h->d_totals);
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
@@ -375,11 +389,14 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     return fail(h, CUB_ERR_INVALID, "iso value %.17g is not representable in the pixel type", p->iso_value);
   compute_step(h);
   const Grid& g = h->g;
+  if ((unsigned long long)g.Y * g.Zl * ((g.Wx + kWordsPerTask - 1) / kWordsPerTask) >= (1ull << 32))
+    return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
   const size_t words = (size_t)g.Zl * g.Y * g.Wp;
   const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
                               h->bits_layout[2] != (uint64_t)g.Zl;
   const bool had = h->bits.p && h->bits.cap >= words;
   CUB_TRY(ensure(h, h->bits, words));
+  CUB_TRY(ensure(h, h->cnt, words));
   CUB_TRY(ensure(h, h->vofs, words));
   CUB_TRY(ensure(h, h->fofs, words));
   if ((!had || layout_changed) && g.Wp != g.Wx) CU_TRY(h, cudaMemsetAsync(h->bits.p, 0, words * 4, h->stream));
@@ -403,8 +420,24 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     Timer t(h, 1);
     CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 2 * n_tiles * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    {
+      // K2a: per-word counts (z-sweep over the scan range)
+      using Smem = SweepSmem<kCountNTX, kCountNTY, MODE_COUNT>;
+      SweepArgs a{};
+      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32;
+      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
+      const int gx = (g.Wx + kCountNTX - 2) / (kCountNTX - 1), gy = (g.Y + kCountNTY - 2) / (kCountNTY - 1);
+      a.tz = pick_tz(gx, gy, a.z_end - a.z_begin);
+      a.counts = h->cnt.p;
+      auto kern = k_sweep<kCountNTX, kCountNTY, MODE_COUNT, uint32_t>;
+      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+      dim3 grid(gx, gy, (a.z_end - a.z_begin + a.tz - 1) / a.tz);
+      kern<<<grid, kCountNTX * kCountNTY, sizeof(Smem), h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
     ScanState st{h->status.p, h->status.p + n_tiles, h->d_ticket, h->d_totals};
-    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(h->bits.p, h->vofs.p, h->fofs.p, g, word_begin,
+    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(h->cnt.p, h->vofs.p, h->fofs.p, g, word_begin,
                                                                     n_words, st);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
@@ -468,16 +501,15 @@ int cub_emit(cub_handle h, int id_bytes) {
   const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
   if (h->n_quads > 0) {
     Timer t(h, 2);
-    EmitArgs a;
+    using Smem = SweepSmem<kEmitNTX, kEmitNTY, MODE_EMIT>;
+    SweepArgs a{};
     a.bits = h->bits.p; a.vofs = h->vofs.p; a.fofs = h->fofs.p;
-    a.g = g; a.geom = h->geom;
-    a.zs0 = h->zs0; a.zs1 = h->zs1; a.owner_z_min = h->owner_z_min;
-    const int gx = (g.Wx + kEmitTX - 1) / kEmitTX, gy = (g.Y + kEmitTY - 1) / kEmitTY;
+    a.g = g; a.geom = h->geom; a.Wc = (g.X + 32) / 32;
+    a.z_begin = h->zs0; a.z_end = h->zs1; a.owner_z_min = h->owner_z_min; a.own_z_top = h->zs1;
+    const int gx = (a.Wc + kEmitNTX - 4) / (kEmitNTX - 3), gy = (g.Y + 1 + kEmitNTY - 4) / (kEmitNTY - 3);
     const int nz = h->zs1 - h->zs0;
-    int tz = 32;
-    while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 4LL * kNumSMs) tz >>= 1;
-    if (tz > nz) tz = nz;
-    a.tz = tz;
+    a.tz = pick_tz(gx, gy, nz);
+    a.ghost_v = (uint32_t)h->ghost_v;
     a.ghost_f = (uint32_t)h->ghost_f;
     a.id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
     a.points = h->points.p;
@@ -487,10 +519,17 @@ int cub_emit(cub_handle h, int id_bytes) {
     a.vol = cd ? h->d_vol : nullptr;
     a.celldata = cd ? h->celldata.p : nullptr;
     a.pix_bytes = h->pix_bytes;
-    dim3 grid(gx, gy, (nz + tz - 1) / tz);
-    constexpr int threads = (kEmitTX + 2) * (kEmitTY + 2);
-    if (id_bytes == 4) k_emit<kEmitTX, kEmitTY, uint32_t><<<grid, threads, 0, h->stream>>>(a);
-    else k_emit<kEmitTX, kEmitTY, unsigned long long><<<grid, threads, 0, h->stream>>>(a);
+    dim3 grid(gx, gy, (nz + a.tz - 1) / a.tz);
+    constexpr int threads = kEmitNTX * kEmitNTY;
+    if (id_bytes == 4) {
+      auto kern = k_sweep<kEmitNTX, kEmitNTY, MODE_EMIT, uint32_t>;
+      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+      kern<<<grid, threads, sizeof(Smem), h->stream>>>(a);
+    } else {
+      auto kern = k_sweep<kEmitNTX, kEmitNTY, MODE_EMIT, unsigned long long>;
+      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
+      kern<<<grid, threads, sizeof(Smem), h->stream>>>(a);
+    }
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();

@@ -1,16 +1,16 @@
-// k_count_scan.cuh — K2: faces / owned corners per 32-voxel word + single-pass exclusive scan.
+// k_count_scan.cuh — K2b: single-pass exclusive scan of the per-word (vertex, face) counts.
 //
 // Replaces, for id assignment, the per-slice vertex lookup of the reference
 // (VertexLookupMap h:273-313, used at txx:186-191): ids follow from an exclusive prefix sum, in
 // voxel-raster order, of "corners first touched by this voxel" (vertex ids, nextVertexId
 // txx:116,189-190) and "faces of this voxel" (cell ids, nextCellId txx:117,197-202).
 //
-// One pass over the bitmask only (N/8 bytes in, 2*N/8 bytes out): each thread handles 4
-// consecutive words (one 16-byte load per neighbour row), counts with popc over the masks of
-// cub_common.cuh, a block-wide scan combines the 1024 words of a tile, and tiles are chained with
-// decoupled look-back (flag+value packed in one 64-bit descriptor per tile and quantity; tile
-// numbers are handed out by an atomic ticket so a tile only ever waits for tiles that started
-// before it).
+// K2a (k_sweep.cuh, MODE_COUNT) leaves one packed count (faces << 16 | vertices) per 32-voxel word.
+// This kernel turns them into the two exclusive-offset arrays vofs / fofs: each thread takes 4
+// consecutive words (one 16-byte load), a block-wide scan combines the 1024 words of a tile, and tiles
+// are chained with decoupled look-back (flag+value packed in one 64-bit descriptor per tile and
+// quantity; tile numbers are handed out by an atomic ticket so a tile only ever waits for tiles that
+// started before it).  HBM-bound: N/8 bytes in, 2*N/8 bytes out.
 #pragma once
 #include "cub_common.cuh"
 
@@ -66,7 +66,7 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long*
 
 // scan range: words [word_begin, word_begin + n_words) of the padded [Zl][Y][Wp] layout (whole slices)
 __global__ void __launch_bounds__(kScanThreads)
-    k_count_scan(const uint32_t* __restrict__ bits, uint32_t* __restrict__ vofs, uint32_t* __restrict__ fofs, Grid g,
+    k_count_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ vofs, uint32_t* __restrict__ fofs, Grid g,
                  size_t word_begin, size_t n_words, ScanState st) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
@@ -84,48 +84,14 @@ __global__ void __launch_bounds__(kScanThreads)
 
   if (gw < n_words) {
     const size_t aw = word_begin + gw;  // absolute padded word index
-    const size_t row = aw / (size_t)g.Wp;
-    const int w4 = (int)(aw - row * (size_t)g.Wp);
-    const int zl = (int)(row / (size_t)g.Y);
-    const int y = (int)(row - (size_t)zl * g.Y);
-    if (w4 < g.Wx) {
-      const uint32_t* rp[3][3];
-      row_pointers(bits, g, y, zl, rp);
-      // six words per neighbour row: [w4-1, w4 .. w4+3, w4+4]
-      uint32_t a[3][3][6];
+    const int w4 = (int)(aw % (size_t)g.Wp);
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(counts + aw));
+    const uint32_t c[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-      for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-          const uint4 q = __ldg(reinterpret_cast<const uint4*>(rp[dz][dy] + w4));
-          a[dz][dy][0] = (w4 > 0) ? __ldg(rp[dz][dy] + w4 - 1) : 0u;
-          a[dz][dy][1] = q.x; a[dz][dy][2] = q.y; a[dz][dy][3] = q.z; a[dz][dy][4] = q.w;
-          a[dz][dy][5] = (w4 + 4 < g.Wx) ? __ldg(rp[dz][dy] + w4 + 4) : 0u;
-        }
-#pragma unroll
-      for (int j = 0; j < kScanWordsPerThread; ++j) {
-        const int w = w4 + j;
-        if (w < g.Wx) {
-          Nbhd nb;
-          const bool first = (w == 0), last = (w == g.Wx - 1);
-#pragma unroll
-          for (int dz = 0; dz < 3; ++dz)
-#pragma unroll
-            for (int dy = 0; dy < 3; ++dy) {
-              nb.n[dz][dy][1] = a[dz][dy][j + 1];
-              shift_lr(a[dz][dy][j + 1], a[dz][dy][j], a[dz][dy][j + 2], first, last, nb.n[dz][dy][0], nb.n[dz][dy][2]);
-            }
-          set_validity(nb, g, w, y, zl);
-          uint32_t F[6], O[8];
-          compute_masks(nb, F, O);
-          uint32_t nf = 0, nv = 0;
-#pragma unroll
-          for (int f = 0; f < 6; ++f) nf += __popc(F[f]);
-#pragma unroll
-          for (int l = 0; l < 8; ++l) nv += __popc(O[l]);
-          cv[j] = nv;
-          cf[j] = nf;
-        }
+    for (int j = 0; j < kScanWordsPerThread; ++j) {
+      if (w4 + j < g.Wx) {  // pad words of a row are never written by K2a
+        cv[j] = c[j] & 0xffffu;
+        cf[j] = c[j] >> 16;
       }
     }
   }
