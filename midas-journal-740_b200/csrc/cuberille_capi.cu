@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -25,10 +26,67 @@ using namespace cub;
 
 namespace {
 
-// thread grids of the sweep kernels (corner words x corner rows per CTA), see k_sweep.cuh
-constexpr int kCountNTX = 16, kCountNTY = 16;  // 15 x 15 voxel words counted per CTA step
-constexpr int kEmitNTX = 16, kEmitNTY = 16;    // 13 x 13 voxel words emitted per CTA step
 constexpr int kNumSMs = 148;
+
+// slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
+int pick_tz(int gx, int gy, int nz) {
+  int tz = 32;
+  while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * kNumSMs) tz >>= 1;
+  if (tz > nz) tz = nz;
+  return tz < 1 ? 1 : tz;
+}
+
+// One instantiation of the sweep kernel (thread grid NTX x NTY, R corner rows per thread; k_sweep.cuh)
+template <typename C, typename IdT>
+cudaError_t launch_sweep(SweepArgs a, int nvox_words_x, int nvox_rows_y, cudaStream_t stream) {
+  using Smem = SweepSmem<C>;
+  auto kern = k_sweep<C, IdT>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
+  if (e != cudaSuccess) return e;
+  const int gx = (nvox_words_x + C::TXW - 1) / C::TXW, gy = (nvox_rows_y + C::TY - 1) / C::TY;
+  const int nz = a.z_end - a.z_begin;
+  a.tz = pick_tz(gx, gy, nz);
+  dim3 grid(gx, gy, (nz + a.tz - 1) / a.tz);
+  kern<<<grid, C::NTP, sizeof(Smem), stream>>>(a);
+  return cudaGetLastError();
+}
+
+int tuning_knob(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+template <typename IdT>
+cudaError_t dispatch_emit(const SweepArgs& a, int wx, int ny, cudaStream_t st) {
+  // wide tiles (16 voxel words) for big volumes, narrow ones (8) when a row has few words
+  const int cfg = tuning_knob("CUB_EMIT_CFG", wx > 8 ? 0 : 10);
+  switch (cfg) {
+    case 0: return launch_sweep<SweepCfg<19, 12, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 1: return launch_sweep<SweepCfg<19, 6, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 2: return launch_sweep<SweepCfg<19, 3, 4, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 3: return launch_sweep<SweepCfg<19, 8, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 4: return launch_sweep<SweepCfg<19, 4, 4, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 5: return launch_sweep<SweepCfg<19, 9, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 6: return launch_sweep<SweepCfg<11, 12, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 7: return launch_sweep<SweepCfg<11, 16, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 8: return launch_sweep<SweepCfg<19, 16, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 9: return launch_sweep<SweepCfg<19, 6, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    case 11: return launch_sweep<SweepCfg<19, 8, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
+    default: return launch_sweep<SweepCfg<11, 6, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
+  }
+}
+
+cudaError_t dispatch_count(const SweepArgs& a, int wx, int ny, cudaStream_t st) {
+  const int cfg = tuning_knob("CUB_COUNT_CFG", wx > 8 ? 1 : 10);
+  switch (cfg) {
+    case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    case 2: return launch_sweep<SweepCfg<17, 15, 4, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    case 3: return launch_sweep<SweepCfg<17, 7, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    case 4: return launch_sweep<SweepCfg<17, 7, 4, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    default: return launch_sweep<SweepCfg<9, 14, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+  }
+}
 
 template <typename P>
 struct DevBuf {
@@ -231,14 +289,6 @@ int setup_grid(cub_handle h) {
   return CUB_OK;
 }
 
-// slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
-int pick_tz(int gx, int gy, int nz) {
-  int tz = 32;
-  while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * kNumSMs) tz >>= 1;
-  if (tz > nz) tz = nz;
-  return tz < 1 ? 1 : tz;
-}
-
 void compute_step(cub_handle h) {
   // txx:75-85: auto step length = max spacing * 0.25
   double ms = h->geom.spacing[0];
@@ -422,19 +472,12 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
     {
       // K2a: per-word counts (z-sweep over the scan range)
-      using Smem = SweepSmem<kCountNTX, kCountNTY, MODE_COUNT>;
       SweepArgs a{};
       a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32;
       a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-      const int gx = (g.Wx + kCountNTX - 2) / (kCountNTX - 1), gy = (g.Y + kCountNTY - 2) / (kCountNTY - 1);
-      a.tz = pick_tz(gx, gy, a.z_end - a.z_begin);
       a.counts = h->cnt.p;
-      auto kern = k_sweep<kCountNTX, kCountNTY, MODE_COUNT, uint32_t>;
-      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-      dim3 grid(gx, gy, (a.z_end - a.z_begin + a.tz - 1) / a.tz);
-      kern<<<grid, kCountNTX * kCountNTY, sizeof(Smem), h->stream>>>(a);
+      CU_TRY(h, dispatch_count(a, g.Wx, g.Y, h->stream));
       h->launches++;
-      CU_TRY(h, cudaGetLastError());
     }
     ScanState st{h->status.p, h->status.p + n_tiles, h->d_ticket, h->d_totals};
     k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(h->cnt.p, h->vofs.p, h->fofs.p, g, word_begin,
@@ -501,15 +544,10 @@ int cub_emit(cub_handle h, int id_bytes) {
   const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
   if (h->n_quads > 0) {
     Timer t(h, 2);
-    using Smem = SweepSmem<kEmitNTX, kEmitNTY, MODE_EMIT>;
     SweepArgs a{};
     a.bits = h->bits.p; a.vofs = h->vofs.p; a.fofs = h->fofs.p;
     a.g = g; a.geom = h->geom; a.Wc = (g.X + 32) / 32;
-    a.z_begin = h->zs0; a.z_end = h->zs1; a.owner_z_min = h->owner_z_min; a.own_z_top = h->zs1;
-    const int gx = (a.Wc + kEmitNTX - 4) / (kEmitNTX - 3), gy = (g.Y + 1 + kEmitNTY - 4) / (kEmitNTY - 3);
-    const int nz = h->zs1 - h->zs0;
-    a.tz = pick_tz(gx, gy, nz);
-    a.ghost_v = (uint32_t)h->ghost_v;
+    a.z_begin = h->zs0; a.z_end = h->zs1; a.owner_z_min = h->owner_z_min;
     a.ghost_f = (uint32_t)h->ghost_f;
     a.id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
     a.points = h->points.p;
@@ -519,17 +557,8 @@ int cub_emit(cub_handle h, int id_bytes) {
     a.vol = cd ? h->d_vol : nullptr;
     a.celldata = cd ? h->celldata.p : nullptr;
     a.pix_bytes = h->pix_bytes;
-    dim3 grid(gx, gy, (nz + a.tz - 1) / a.tz);
-    constexpr int threads = kEmitNTX * kEmitNTY;
-    if (id_bytes == 4) {
-      auto kern = k_sweep<kEmitNTX, kEmitNTY, MODE_EMIT, uint32_t>;
-      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-      kern<<<grid, threads, sizeof(Smem), h->stream>>>(a);
-    } else {
-      auto kern = k_sweep<kEmitNTX, kEmitNTY, MODE_EMIT, unsigned long long>;
-      CU_TRY(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)));
-      kern<<<grid, threads, sizeof(Smem), h->stream>>>(a);
-    }
+    if (id_bytes == 4) CU_TRY(h, dispatch_emit<uint32_t>(a, g.Wx, g.Y, h->stream));
+    else CU_TRY(h, dispatch_emit<unsigned long long>(a, g.Wx, g.Y, h->stream));
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();

@@ -6,8 +6,8 @@
 // txx:116,189-190) and "faces of this voxel" (cell ids, nextCellId txx:117,197-202).
 //
 // K2a (k_sweep.cuh, MODE_COUNT) leaves one packed count (faces << 16 | vertices) per 32-voxel word.
-// This kernel turns them into the two exclusive-offset arrays vofs / fofs: each thread takes 4
-// consecutive words (one 16-byte load), a block-wide scan combines the 1024 words of a tile, and tiles
+// This kernel turns them into the two exclusive-offset arrays vofs / fofs: each thread takes 16
+// consecutive words (four 16-byte loads), a block-wide scan combines the 4096 words of a tile, and tiles
 // are chained with decoupled look-back (flag+value packed in one 64-bit descriptor per tile and
 // quantity; tile numbers are handed out by an atomic ticket so a tile only ever waits for tiles that
 // started before it).  HBM-bound: N/8 bytes in, 2*N/8 bytes out.
@@ -17,7 +17,7 @@
 namespace cub {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanWordsPerThread = 4;
+constexpr int kScanWordsPerThread = 16;
 constexpr int kScanTileWords = kScanThreads * kScanWordsPerThread;
 
 constexpr uint64_t kFlagShift = 62;
@@ -83,20 +83,26 @@ __global__ void __launch_bounds__(kScanThreads)
   for (int j = 0; j < kScanWordsPerThread; ++j) cv[j] = cf[j] = 0;
 
   if (gw < n_words) {
-    const size_t aw = word_begin + gw;  // absolute padded word index
-    const int w4 = (int)(aw % (size_t)g.Wp);
-    const uint4 q = __ldg(reinterpret_cast<const uint4*>(counts + aw));
-    const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+    const size_t aw = word_begin + gw;  // absolute padded word index (a multiple of 4; rows are Wp = 4k words)
+    const int w0 = (int)(aw % (size_t)g.Wp);
 #pragma unroll
-    for (int j = 0; j < kScanWordsPerThread; ++j) {
-      if (w4 + j < g.Wx) {  // pad words of a row are never written by K2a
-        cv[j] = c[j] & 0xffffu;
-        cf[j] = c[j] >> 16;
+    for (int v4 = 0; v4 < kScanWordsPerThread / 4; ++v4) {
+      if (gw + 4 * v4 < n_words) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(counts + aw) + v4);
+        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int w = (w0 + 4 * v4 + j) % g.Wp;
+          if (w < g.Wx) {  // pad words of a row are never written by K2a
+            cv[4 * v4 + j] = c[j] & 0xffffu;
+            cf[4 * v4 + j] = c[j] >> 16;
+          }
+        }
       }
     }
   }
 
-  // thread totals packed as (faces << 32 | vertices); a tile holds < 2^18 of either
+  // thread totals packed as (faces << 32 | vertices); a tile holds < 2^20 of either
   unsigned long long mine = 0;
 #pragma unroll
   for (int j = 0; j < kScanWordsPerThread; ++j) mine += ((unsigned long long)cf[j] << 32) | cv[j];
@@ -146,14 +152,19 @@ __global__ void __launch_bounds__(kScanThreads)
     const unsigned long long excl = warp_excl + (incl - mine);
     uint32_t v = (uint32_t)(s_excl_v + (excl & 0xffffffffull));
     uint32_t f = (uint32_t)(s_excl_f + (excl >> 32));
-    uint4 ov, of;
-    ov.x = v; of.x = f; v += cv[0]; f += cf[0];
-    ov.y = v; of.y = f; v += cv[1]; f += cf[1];
-    ov.z = v; of.z = f; v += cv[2]; f += cf[2];
-    ov.w = v; of.w = f;
     const size_t aw = word_begin + gw;
-    *reinterpret_cast<uint4*>(vofs + aw) = ov;
-    *reinterpret_cast<uint4*>(fofs + aw) = of;
+#pragma unroll
+    for (int v4 = 0; v4 < kScanWordsPerThread / 4; ++v4) {
+      if (gw + 4 * v4 < n_words) {
+        uint4 ov, of;
+        ov.x = v; of.x = f; v += cv[4 * v4 + 0]; f += cf[4 * v4 + 0];
+        ov.y = v; of.y = f; v += cv[4 * v4 + 1]; f += cf[4 * v4 + 1];
+        ov.z = v; of.z = f; v += cv[4 * v4 + 2]; f += cf[4 * v4 + 2];
+        ov.w = v; of.w = f; v += cv[4 * v4 + 3]; f += cf[4 * v4 + 3];
+        reinterpret_cast<uint4*>(vofs + aw)[v4] = ov;
+        reinterpret_cast<uint4*>(fofs + aw)[v4] = of;
+      }
+    }
   }
 }
 
