@@ -19,8 +19,10 @@
 #include "k_classify.cuh"
 #include "k_count_scan.cuh"
 #include "k_generate.cuh"
+#include "k_faces.cuh"
 #include "k_project.cuh"
 #include "k_sweep.cuh"
+#include "k_vertices.cuh"
 
 using namespace cub;
 
@@ -37,13 +39,11 @@ int pick_tz(int gx, int gy, int nz) {
 }
 
 // One instantiation of the sweep kernel (thread grid NTX x NTY, R corner rows per thread; k_sweep.cuh)
-template <typename C, typename IdT>
-cudaError_t launch_sweep(SweepArgs a, int nvox_words_x, int nvox_rows_y, cudaStream_t stream) {
+template <typename C>
+cudaError_t launch_sweep(SweepArgs a, cudaStream_t stream) {
   using Smem = SweepSmem<C>;
-  auto kern = k_sweep<C, IdT>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem));
-  if (e != cudaSuccess) return e;
-  const int gx = (nvox_words_x + C::TXW - 1) / C::TXW, gy = (nvox_rows_y + C::TY - 1) / C::TY;
+  auto kern = k_sweep<C>;
+  const int gx = (a.g.Wx + C::TXW - 1) / C::TXW, gy = (a.g.Y + C::TY - 1) / C::TY;
   const int nz = a.z_end - a.z_begin;
   a.tz = pick_tz(gx, gy, nz);
   dim3 grid(gx, gy, (nz + a.tz - 1) / a.tz);
@@ -56,35 +56,16 @@ int tuning_knob(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 
-template <typename IdT>
-cudaError_t dispatch_emit(const SweepArgs& a, int wx, int ny, cudaStream_t st) {
-  // wide tiles (16 voxel words) for big volumes, narrow ones (8) when a row has few words
-  const int cfg = tuning_knob("CUB_EMIT_CFG", wx > 8 ? 0 : 10);
+template <int MODE>
+cudaError_t dispatch_sweep(const SweepArgs& a, cudaStream_t st) {
+  // wide tiles (16 voxel words per row) for big volumes, narrow ones (8) when a row has few words
+  const int cfg = tuning_knob(MODE == MODE_COUNT ? "CUB_COUNT_CFG" : "CUB_ASSIGN_CFG", a.g.Wx > 8 ? 1 : 10);
   switch (cfg) {
-    case 0: return launch_sweep<SweepCfg<19, 12, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 1: return launch_sweep<SweepCfg<19, 6, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 2: return launch_sweep<SweepCfg<19, 3, 4, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 3: return launch_sweep<SweepCfg<19, 8, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 4: return launch_sweep<SweepCfg<19, 4, 4, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 5: return launch_sweep<SweepCfg<19, 9, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 6: return launch_sweep<SweepCfg<11, 12, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 7: return launch_sweep<SweepCfg<11, 16, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 8: return launch_sweep<SweepCfg<19, 16, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 9: return launch_sweep<SweepCfg<19, 6, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    case 11: return launch_sweep<SweepCfg<19, 8, 1, MODE_EMIT>, IdT>(a, wx, ny, st);
-    default: return launch_sweep<SweepCfg<11, 6, 2, MODE_EMIT>, IdT>(a, wx, ny, st);
-  }
-}
-
-cudaError_t dispatch_count(const SweepArgs& a, int wx, int ny, cudaStream_t st) {
-  const int cfg = tuning_knob("CUB_COUNT_CFG", wx > 8 ? 1 : 10);
-  switch (cfg) {
-    case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE_COUNT>, uint32_t>(a, wx, ny, st);
-    case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
-    case 2: return launch_sweep<SweepCfg<17, 15, 4, MODE_COUNT>, uint32_t>(a, wx, ny, st);
-    case 3: return launch_sweep<SweepCfg<17, 7, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
-    case 4: return launch_sweep<SweepCfg<17, 7, 4, MODE_COUNT>, uint32_t>(a, wx, ny, st);
-    default: return launch_sweep<SweepCfg<9, 14, 2, MODE_COUNT>, uint32_t>(a, wx, ny, st);
+    case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE>>(a, st);
+    case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE>>(a, st);
+    case 2: return launch_sweep<SweepCfg<17, 7, 2, MODE>>(a, st);
+    case 3: return launch_sweep<SweepCfg<17, 7, 4, MODE>>(a, st);
+    default: return launch_sweep<SweepCfg<9, 14, 2, MODE>>(a, st);
   }
 }
 
@@ -113,7 +94,11 @@ struct cub_handle_s {
   uint64_t image_nz = 0, local_z0 = 0, own_z0 = 0, own_z1 = 0;
 
   // scratch
-  DevBuf<uint32_t> bits, cnt, vofs, fofs;
+  DevBuf<uint32_t> bits, cnt, act, vofs, fofs, cofs, perm;
+  DevBuf<uint2> vtx;
+  uint64_t ent_layout[3] = {0, 0, 0};
+  int EY = 0, EW = 0;
+  uint64_t n_active = 0;
   uint64_t bits_layout[3] = {0, 0, 0};
   DevBuf<unsigned long long> status;  // 2 * n_tiles
   unsigned int* d_ticket = nullptr;
@@ -331,8 +316,8 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->own_stream = true;
   }
   bool ok = cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
-            cudaMalloc(&h->d_totals, 6 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMallocHost(&h->h_totals, 6 * sizeof(unsigned long long)) == cudaSuccess;
+            cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost(&h->h_totals, 8 * sizeof(unsigned long long)) == cudaSuccess;
   for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
   cub_default_params(&h->params);
@@ -345,7 +330,7 @@ int cub_destroy(cub_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
-  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
+  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
   cudaFree(h->d_ticket); cudaFree(h->d_totals);
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
@@ -441,16 +426,29 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   const Grid& g = h->g;
   if ((unsigned long long)g.Y * g.Zl * ((g.Wx + kWordsPerTask - 1) / kWordsPerTask) >= (1ull << 32))
     return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
+  if (g.X > 65534 || g.Y > 65534) return fail(h, CUB_ERR_UNSUPPORTED, "x / y size above 65534 voxels is not supported");
   const size_t words = (size_t)g.Zl * g.Y * g.Wp;
   const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
                               h->bits_layout[2] != (uint64_t)g.Zl;
   const bool had = h->bits.p && h->bits.cap >= words;
   CUB_TRY(ensure(h, h->bits, words));
-  CUB_TRY(ensure(h, h->cnt, words));
-  CUB_TRY(ensure(h, h->vofs, words));
-  CUB_TRY(ensure(h, h->fofs, words));
   if ((!had || layout_changed) && g.Wp != g.Wx) CU_TRY(h, cudaMemsetAsync(h->bits.p, 0, words * 4, h->stream));
   h->bits_layout[0] = g.X; h->bits_layout[1] = g.Y; h->bits_layout[2] = g.Zl;
+  // entry lattice of the counts / offsets / active masks: one entry per corner word, (Zl+1) x (Y+1) x EW
+  const int Wc = (g.X + 32) / 32;
+  h->EY = g.Y + 1;
+  h->EW = (Wc + 1 + 3) & ~3;
+  const size_t plane_entries = (size_t)h->EY * h->EW;
+  const size_t entries = plane_entries * (size_t)(g.Zl + 1);
+  if (entries + kScanTile >= (1ull << 32)) return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
+  const bool had_e = h->cnt.p && h->cnt.cap >= entries;
+  CUB_TRY(ensure(h, h->cnt, entries));
+  CUB_TRY(ensure(h, h->act, entries + 4));
+  CUB_TRY(ensure(h, h->vofs, entries));
+  CUB_TRY(ensure(h, h->fofs, entries));
+  CUB_TRY(ensure(h, h->cofs, entries + 4));
+  // entries that K2a never writes (padding columns) must read as zero counts
+  if (!had_e || layout_changed) CU_TRY(h, cudaMemsetAsync(h->cnt.p, 0, entries * 4, h->stream));
 
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
 
@@ -461,36 +459,41 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     CU_TRY(h, cudaGetLastError());
     t.stop();
   }
-  // K2
-  const size_t word_begin = (size_t)h->owner_z_min * g.Y * g.Wp;
-  const size_t n_words = (size_t)(h->zs1 - h->owner_z_min) * g.Y * g.Wp;
-  const size_t n_tiles = (n_words + kScanTileWords - 1) / kScanTileWords;
-  CUB_TRY(ensure(h, h->status, 2 * n_tiles));
+  // K2: scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
+  const size_t e_begin = (size_t)h->owner_z_min * plane_entries;
+  const size_t n_scan = (size_t)(h->zs1 + 1 - h->owner_z_min) * plane_entries;
+  const size_t n_tiles = (n_scan + kScanTile - 1) / kScanTile;
+  CUB_TRY(ensure(h, h->status, 3 * n_tiles));
   {
     Timer t(h, 1);
-    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 2 * n_tiles * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
     CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
     {
-      // K2a: per-word counts (z-sweep over the scan range)
+      // K2a: per-entry counts + active-corner masks (z-sweep over the scan range)
       SweepArgs a{};
-      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32;
+      a.bits = h->bits.p; a.g = g; a.Wc = Wc; a.EY = h->EY; a.EW = h->EW;
       a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-      a.counts = h->cnt.p;
-      CU_TRY(h, dispatch_count(a, g.Wx, g.Y, h->stream));
+      a.cnt = h->cnt.p; a.act = h->act.p;
+      CU_TRY(h, dispatch_sweep<MODE_COUNT>(a, h->stream));
       h->launches++;
     }
-    ScanState st{h->status.p, h->status.p + n_tiles, h->d_ticket, h->d_totals};
-    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(h->cnt.p, h->vofs.p, h->fofs.p, g, word_begin,
-                                                                    n_words, st);
+    if (h->timing) cudaEventRecord(h->ev[6], h->stream);
+    ScanArgs sa{};
+    sa.cnt = h->cnt.p; sa.vofs = h->vofs.p; sa.fofs = h->fofs.p; sa.cofs = h->cofs.p;
+    sa.e_begin = e_begin; sa.n = n_scan;
+    sa.plane_entries = (unsigned)plane_entries; sa.plane_lo = (unsigned)h->zs0;
+    sa.status = h->status.p; sa.n_tiles = (unsigned)n_tiles; sa.ticket = h->d_ticket; sa.totals = h->d_totals;
+    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
-    const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * g.Y * g.Wp : (size_t)-1;
-    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, mark0, (size_t)-1, h->d_totals);
+    const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * plane_entries : (size_t)-1;
+    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, mark0, h->d_totals);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();
+    if (h->timing) cudaEventElapsedTime(&h->ms[7], h->ev[6], h->ev[1]);  // the scan alone
   }
-  CU_TRY(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  CU_TRY(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->timing) {
     cudaEventRecord(h->ev[3], h->stream);
@@ -501,8 +504,9 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   if (tot_v >= (1ull << 32) || tot_f >= (1ull << 32))
     return fail(h, CUB_ERR_OVERFLOW, "more than 2^32 vertices or faces in one handle (%llu, %llu): split into z-slabs",
                 (unsigned long long)tot_v, (unsigned long long)tot_f);
-  h->ghost_v = h->h_totals[2];
-  h->ghost_f = h->h_totals[3];
+  h->n_active = h->h_totals[2];
+  h->ghost_v = h->h_totals[3];
+  h->ghost_f = h->h_totals[4];
   h->n_points = tot_v - h->ghost_v;
   h->n_quads = tot_f - h->ghost_f;
   h->point_base = h->cell_base = 0;
@@ -537,30 +541,56 @@ int cub_emit(cub_handle h, int id_bytes) {
   const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
   CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
   CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
+  CUB_TRY(ensure(h, h->vtx, n_pts_all));
+  CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
   if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
   if (cd) CUB_TRY(ensure(h, h->celldata, (size_t)h->n_cells * h->pix_bytes));
 
   if (h->timing) cudaEventRecord(h->ev[4], h->stream);
   const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
+  const unsigned long long id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
   if (h->n_quads > 0) {
     Timer t(h, 2);
-    SweepArgs a{};
-    a.bits = h->bits.p; a.vofs = h->vofs.p; a.fofs = h->fofs.p;
-    a.g = g; a.geom = h->geom; a.Wc = (g.X + 32) / 32;
-    a.z_begin = h->zs0; a.z_end = h->zs1; a.owner_z_min = h->owner_z_min;
-    a.ghost_f = (uint32_t)h->ghost_f;
-    a.id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
-    a.points = h->points.p;
-    a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
-    a.mode = mode;
-    a.emit_ghost_points = ghost_points ? 1 : 0;
-    a.vol = cd ? h->d_vol : nullptr;
-    a.celldata = cd ? h->celldata.p : nullptr;
-    a.pix_bytes = h->pix_bytes;
-    if (id_bytes == 4) CU_TRY(h, dispatch_emit<uint32_t>(a, g.Wx, g.Y, h->stream));
-    else CU_TRY(h, dispatch_emit<unsigned long long>(a, g.Wx, g.Y, h->stream));
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
+    {
+      // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
+      SweepArgs a{};
+      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
+      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
+      a.vofs = h->vofs.p; a.vtx = h->vtx.p;
+      CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
+      h->launches++;
+    }
+    {
+      // K3b: points + corner -> id map
+      VertexArgs a{};
+      a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
+      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
+      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
+      a.points = h->points.p; a.perm = h->perm.p;
+      k_vertices<<<(unsigned)((n_pts_all + 255) / 256), 256, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
+    {
+      // K3c: faces
+      FaceArgs a{};
+      a.bits = h->bits.p; a.g = g; a.EY = h->EY; a.EW = h->EW;
+      a.z_begin = h->zs0; a.z_end = h->zs1;
+      a.fofs = h->fofs.p; a.act = h->act.p; a.cofs = h->cofs.p; a.perm = h->perm.p;
+      a.ghost_f = (uint32_t)h->ghost_f;
+      a.id_delta = id_delta;
+      a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
+      a.mode = mode;
+      a.vol = cd ? h->d_vol : nullptr;
+      a.celldata = cd ? h->celldata.p : nullptr;
+      a.pix_bytes = h->pix_bytes;
+      const size_t nthreads = (size_t)g.Y * g.Wp * (size_t)(h->zs1 - h->zs0);
+      const unsigned blocks = (unsigned)((nthreads + 255) / 256);
+      if (id_bytes == 4) k_faces<uint32_t><<<blocks, 256, 0, h->stream>>>(a);
+      else k_faces<unsigned long long><<<blocks, 256, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
     t.stop();
   }
   if (proj && h->n_points > 0) {
@@ -572,7 +602,7 @@ int cub_emit(cub_handle h, int id_bytes) {
   if (mode == kEmitScratchQuads && h->n_quads > 0) {
     Timer t(h, 4);
     const unsigned blocks = (unsigned)((h->n_quads + 255) / 256);
-    const unsigned long long delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
+    const unsigned long long delta = id_delta;
     if (id_bytes == 4)
       k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, (size_t)h->n_quads, delta);
     else

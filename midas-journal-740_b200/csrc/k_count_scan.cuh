@@ -1,35 +1,44 @@
-// k_count_scan.cuh — K2b: single-pass exclusive scan of the per-word (vertex, face) counts.
+// k_count_scan.cuh — K2b: single-pass exclusive scan of the per-entry (vertex, face, active-corner) counts.
 //
 // Replaces, for id assignment, the per-slice vertex lookup of the reference
 // (VertexLookupMap h:273-313, used at txx:186-191): ids follow from an exclusive prefix sum, in
 // voxel-raster order, of "corners first touched by this voxel" (vertex ids, nextVertexId
-// txx:116,189-190) and "faces of this voxel" (cell ids, nextCellId txx:117,197-202).
+// txx:116,189-190) and "faces of this voxel" (cell ids, nextCellId txx:117,197-202).  The third
+// quantity, active corners per corner word in corner-raster order, indexes the corner -> id map.
 //
-// K2a (k_sweep.cuh, MODE_COUNT) leaves one packed count (faces << 16 | vertices) per 32-voxel word.
-// This kernel turns them into the two exclusive-offset arrays vofs / fofs: each thread takes 16
-// consecutive words (four 16-byte loads), a block-wide scan combines the 4096 words of a tile, and tiles
-// are chained with decoupled look-back (flag+value packed in one 64-bit descriptor per tile and
-// quantity; tile numbers are handed out by an atomic ticket so a tile only ever waits for tiles that
-// started before it).  HBM-bound: N/8 bytes in, 2*N/8 bytes out.
+// K2a (k_sweep.cuh, MODE_COUNT) leaves one packed count per entry of the [Zl+1][EY][EW] lattice
+// (owned corners | faces << 10 | active corners << 20).  This kernel turns them into the three
+// exclusive-offset arrays vofs / fofs / cofs: each thread takes 16 consecutive entries (four 16-byte
+// loads), a block-wide scan combines the 4096 entries of a tile (the three counts travel packed in one
+// 64-bit word, 21 bits each), and tiles are chained with decoupled look-back (flag+value packed in one
+// 64-bit descriptor per tile and quantity; tile numbers are handed out by an atomic ticket so a tile only
+// ever waits for tiles that started before it).  HBM-bound: 4 bytes in, 12 bytes out per entry.
 #pragma once
 #include "cub_common.cuh"
 
 namespace cub {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanWordsPerThread = 16;
-constexpr int kScanTileWords = kScanThreads * kScanWordsPerThread;
+constexpr int kScanPerThread = 16;
+constexpr int kScanTile = kScanThreads * kScanPerThread;
 
 constexpr uint64_t kFlagShift = 62;
 constexpr uint64_t kFlagAggregate = 1ull << kFlagShift;
 constexpr uint64_t kFlagPrefix = 2ull << kFlagShift;
 constexpr uint64_t kValueMask = (1ull << kFlagShift) - 1ull;
 
-struct ScanState {
-  unsigned long long* status_v;  // [n_tiles] descriptors, vertices
-  unsigned long long* status_f;  // [n_tiles] descriptors, faces
-  unsigned int* ticket;          // tile ticket counter
-  unsigned long long* totals;    // [0] = vertices, [1] = faces in the scan range
+struct ScanArgs {
+  const uint32_t* cnt;
+  uint32_t* vofs;
+  uint32_t* fofs;
+  uint32_t* cofs;
+  size_t e_begin, n;             // scanned entries [e_begin, e_begin + n): whole planes of the lattice
+  unsigned plane_entries;        // EY * EW
+  unsigned plane_lo;             // active corners are counted from this local plane on (ghost plane below: not)
+  unsigned long long* status;    // [3][n_tiles] descriptors
+  unsigned n_tiles;
+  unsigned int* ticket;
+  unsigned long long* totals;    // [0] vertices, [1] faces, [2] active corners of the scanned range
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
@@ -64,48 +73,41 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long*
   return exclusive;
 }
 
-// scan range: words [word_begin, word_begin + n_words) of the padded [Zl][Y][Wp] layout (whole slices)
-__global__ void __launch_bounds__(kScanThreads)
-    k_count_scan(const uint32_t* __restrict__ counts, uint32_t* __restrict__ vofs, uint32_t* __restrict__ fofs, Grid g,
-                 size_t word_begin, size_t n_words, ScanState st) {
+__global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
-  __shared__ unsigned long long s_excl_v, s_excl_f;
+  __shared__ unsigned long long s_excl[3];
 
-  if (threadIdx.x == 0) s_tile = atomicAdd(st.ticket, 1u);
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const int tile = (int)s_tile;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  const size_t gw = (size_t)tile * kScanTileWords + (size_t)threadIdx.x * kScanWordsPerThread;  // within the range
-  uint32_t cv[kScanWordsPerThread], cf[kScanWordsPerThread];
+  const size_t g0 = (size_t)tile * kScanTile + (size_t)threadIdx.x * kScanPerThread;  // within the range
+  uint32_t c[kScanPerThread];
 #pragma unroll
-  for (int j = 0; j < kScanWordsPerThread; ++j) cv[j] = cf[j] = 0;
-
-  if (gw < n_words) {
-    const size_t aw = word_begin + gw;  // absolute padded word index (a multiple of 4; rows are Wp = 4k words)
-    const int w0 = (int)(aw % (size_t)g.Wp);
+  for (int j = 0; j < kScanPerThread; ++j) c[j] = 0;
+  if (g0 < a.n) {
+    const size_t e = a.e_begin + g0;  // absolute entry index, a multiple of 4 (EW is)
 #pragma unroll
-    for (int v4 = 0; v4 < kScanWordsPerThread / 4; ++v4) {
-      if (gw + 4 * v4 < n_words) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(counts + aw) + v4);
-        const uint32_t c[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int w = (w0 + 4 * v4 + j) % g.Wp;
-          if (w < g.Wx) {  // pad words of a row are never written by K2a
-            cv[4 * v4 + j] = c[j] & 0xffffu;
-            cf[4 * v4 + j] = c[j] >> 16;
-          }
-        }
+    for (int v4 = 0; v4 < kScanPerThread / 4; ++v4) {
+      if (g0 + 4 * v4 < a.n) {
+        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.cnt + e) + v4);
+        // a 4-entry group never straddles planes; active corners below plane_lo belong to the slab underneath
+        const bool ghost = (unsigned)((e + 4 * v4) / a.plane_entries) < a.plane_lo;
+        const uint32_t keep = ghost ? 0xfffffu : 0xffffffffu;
+        c[4 * v4 + 0] = q.x & keep; c[4 * v4 + 1] = q.y & keep; c[4 * v4 + 2] = q.z & keep; c[4 * v4 + 3] = q.w & keep;
       }
     }
   }
-
-  // thread totals packed as (faces << 32 | vertices); a tile holds < 2^20 of either
+  // three 21-bit fields in one 64-bit word: vertices | faces << 21 | active corners << 42
+  auto widen = [](uint32_t p) {
+    return (unsigned long long)(p & 0x3ffu) | ((unsigned long long)((p >> 10) & 0x3ffu) << 21) |
+           ((unsigned long long)(p >> 20) << 42);
+  };
   unsigned long long mine = 0;
 #pragma unroll
-  for (int j = 0; j < kScanWordsPerThread; ++j) mine += ((unsigned long long)cf[j] << 32) | cv[j];
+  for (int j = 0; j < kScanPerThread; ++j) mine += widen(c[j]);
   unsigned long long incl = mine;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -121,61 +123,63 @@ __global__ void __launch_bounds__(kScanThreads)
     if (i < warp) warp_excl += t;
     block_total += t;
   }
-  const unsigned long long agg_v = block_total & 0xffffffffull, agg_f = block_total >> 32;
+  const unsigned long long agg[3] = {block_total & 0x1fffffull, (block_total >> 21) & 0x1fffffull, block_total >> 42};
 
   if (warp == 0) {
     if (lane == 0) {
-      st_relaxed(st.status_v + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg_v);
-      st_relaxed(st.status_f + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg_f);
+#pragma unroll
+      for (int k = 0; k < 3; ++k)
+        st_relaxed(a.status + (size_t)k * a.n_tiles + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg[k]);
     }
-    unsigned long long ev = 0, ef = 0;
+    unsigned long long ex[3] = {0, 0, 0};
     if (tile > 0) {
-      ev = lookback(st.status_v, tile, lane);
-      ef = lookback(st.status_f, tile, lane);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ex[k] = lookback(a.status + (size_t)k * a.n_tiles, tile, lane);
       if (lane == 0) {
-        st_relaxed(st.status_v + tile, kFlagPrefix | (ev + agg_v));
-        st_relaxed(st.status_f + tile, kFlagPrefix | (ef + agg_f));
+#pragma unroll
+        for (int k = 0; k < 3; ++k) st_relaxed(a.status + (size_t)k * a.n_tiles + tile, kFlagPrefix | (ex[k] + agg[k]));
       }
     }
     if (lane == 0) {
-      s_excl_v = ev;
-      s_excl_f = ef;
-      if ((size_t)(tile + 1) * kScanTileWords >= n_words) {  // last tile: grand totals
-        st.totals[0] = ev + agg_v;
-        st.totals[1] = ef + agg_f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) s_excl[k] = ex[k];
+      if ((size_t)(tile + 1) * kScanTile >= a.n) {  // last tile: grand totals
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.totals[k] = ex[k] + agg[k];
       }
     }
   }
   __syncthreads();
 
-  if (gw < n_words) {
+  if (g0 < a.n) {
     const unsigned long long excl = warp_excl + (incl - mine);
-    uint32_t v = (uint32_t)(s_excl_v + (excl & 0xffffffffull));
-    uint32_t f = (uint32_t)(s_excl_f + (excl >> 32));
-    const size_t aw = word_begin + gw;
+    uint32_t v = (uint32_t)(s_excl[0] + (excl & 0x1fffffull));
+    uint32_t f = (uint32_t)(s_excl[1] + ((excl >> 21) & 0x1fffffull));
+    uint32_t k = (uint32_t)(s_excl[2] + (excl >> 42));
+    const size_t e = a.e_begin + g0;
 #pragma unroll
-    for (int v4 = 0; v4 < kScanWordsPerThread / 4; ++v4) {
-      if (gw + 4 * v4 < n_words) {
-        uint4 ov, of;
-        ov.x = v; of.x = f; v += cv[4 * v4 + 0]; f += cf[4 * v4 + 0];
-        ov.y = v; of.y = f; v += cv[4 * v4 + 1]; f += cf[4 * v4 + 1];
-        ov.z = v; of.z = f; v += cv[4 * v4 + 2]; f += cf[4 * v4 + 2];
-        ov.w = v; of.w = f; v += cv[4 * v4 + 3]; f += cf[4 * v4 + 3];
-        reinterpret_cast<uint4*>(vofs + aw)[v4] = ov;
-        reinterpret_cast<uint4*>(fofs + aw)[v4] = of;
+    for (int v4 = 0; v4 < kScanPerThread / 4; ++v4) {
+      if (g0 + 4 * v4 < a.n) {
+        uint4 ov, of, ok;
+#define CUB_STEP(field, j)                                   \
+        ov.field = v; of.field = f; ok.field = k;            \
+        v += c[4 * v4 + j] & 0x3ffu; f += (c[4 * v4 + j] >> 10) & 0x3ffu; k += c[4 * v4 + j] >> 20;
+        CUB_STEP(x, 0) CUB_STEP(y, 1) CUB_STEP(z, 2) CUB_STEP(w, 3)
+#undef CUB_STEP
+        reinterpret_cast<uint4*>(a.vofs + e)[v4] = ov;
+        reinterpret_cast<uint4*>(a.fofs + e)[v4] = of;
+        reinterpret_cast<uint4*>(a.cofs + e)[v4] = ok;
       }
     }
   }
 }
 
-// reads the exclusive offsets at up to 2 word positions (slab own-range boundaries)
+// reads the exclusive offsets at the first own entry (slab runs: what the ghost slice below contributed)
 __global__ void k_gather_marks(const uint32_t* __restrict__ vofs, const uint32_t* __restrict__ fofs, size_t mark0,
-                               size_t mark1, unsigned long long* out /* [2..5] */) {
+                               unsigned long long* out /* [3..4] */) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
-    out[2] = (mark0 != (size_t)-1) ? vofs[mark0] : 0ull;
-    out[3] = (mark0 != (size_t)-1) ? fofs[mark0] : 0ull;
-    out[4] = (mark1 != (size_t)-1) ? vofs[mark1] : ~0ull;
-    out[5] = (mark1 != (size_t)-1) ? fofs[mark1] : ~0ull;
+    out[3] = (mark0 != (size_t)-1) ? vofs[mark0] : 0ull;
+    out[4] = (mark0 != (size_t)-1) ? fofs[mark0] : 0ull;
   }
 }
 
