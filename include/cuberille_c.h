@@ -177,8 +177,9 @@ int cub_generate_volume(cub_handle h, int kind, const uint64_t dims[3],
 int cub_download_volume(cub_handle h, void *out, uint64_t bytes);
 
 /* Per-kernel device times (ms, CUDA events on the handle's stream) of the last
- * cub_count/cub_emit: [0]=classify [1]=count+scan [2]=emit [3]=project
- * [4]=triangle split [5]=total count phase [6]=total emit phase.  Only filled
+ * cub_count/cub_emit: [0]=classify [1]=count sweep + scan [2]=emit (assign sweep,
+ * vertices, faces) [3]=project [4]=triangle split [5]=total count phase
+ * [6]=total emit phase [7]=the look-back scan alone.  Only filled
  * when timing was enabled with cub_enable_timing(h, 1) (adds event records and
  * one synchronize per phase; off by default).                                  */
 int cub_enable_timing(cub_handle h, int on);

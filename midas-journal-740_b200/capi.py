@@ -244,8 +244,8 @@ class Handle:
     def timings(self) -> dict:
         ms = (C.c_float * 8)()
         self._check(self._L.cub_get_timings(self._h, ms))
-        names = ["classify", "count_scan", "emit", "project", "split", "count_phase", "emit_phase", "_"]
-        return {n: float(v) for n, v in zip(names, ms) if n != "_"}
+        names = ["classify", "count_scan", "emit", "project", "split", "count_phase", "emit_phase", "scan_only"]
+        return {n: float(v) for n, v in zip(names, ms)}
 
     def launch_count(self) -> int:
         return int(self._L.cub_launch_count(self._h))

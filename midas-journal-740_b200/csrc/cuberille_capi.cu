@@ -6,6 +6,7 @@
 // Everything is ordered on one CUDA stream.  There is no CPU implementation behind this file.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -426,6 +427,7 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   const Grid& g = h->g;
   if ((unsigned long long)g.Y * g.Zl * ((g.Wx + kWordsPerTask - 1) / kWordsPerTask) >= (1ull << 32))
     return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
+  if ((unsigned long long)g.Y * g.Wp >= (1ull << 31)) return fail(h, CUB_ERR_UNSUPPORTED, "x*y too large");
   if (g.X > 65534 || g.Y > 65534) return fail(h, CUB_ERR_UNSUPPORTED, "x / y size above 65534 voxels is not supported");
   const size_t words = (size_t)g.Zl * g.Y * g.Wp;
   const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
@@ -483,7 +485,8 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     sa.e_begin = e_begin; sa.n = n_scan;
     sa.plane_entries = (unsigned)plane_entries; sa.plane_lo = (unsigned)h->zs0;
     sa.status = h->status.p; sa.n_tiles = (unsigned)n_tiles; sa.ticket = h->d_ticket; sa.totals = h->d_totals;
-    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
+    const unsigned scan_ctas = (unsigned)std::min<size_t>(n_tiles, (size_t)kNumSMs * tuning_knob("CUB_SCAN_CTAS_PER_SM", 4));
+    k_count_scan<<<scan_ctas, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * plane_entries : (size_t)-1;
@@ -584,10 +587,12 @@ int cub_emit(cub_handle h, int id_bytes) {
       a.vol = cd ? h->d_vol : nullptr;
       a.celldata = cd ? h->celldata.p : nullptr;
       a.pix_bytes = h->pix_bytes;
-      const size_t nthreads = (size_t)g.Y * g.Wp * (size_t)(h->zs1 - h->zs0);
-      const unsigned blocks = (unsigned)((nthreads + 255) / 256);
-      if (id_bytes == 4) k_faces<uint32_t><<<blocks, 256, 0, h->stream>>>(a);
-      else k_faces<unsigned long long><<<blocks, 256, 0, h->stream>>>(a);
+      const dim3 blocks((g.Wx + 31) / 32, (g.Y + kFaceThreads / 32 - 1) / (kFaceThreads / 32), h->zs1 - h->zs0);
+      if (mode == kEmitScratchQuads) k_faces<uint32_t, kEmitScratchQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
+      else if (mode == kEmitQuads && id_bytes == 4) k_faces<uint32_t, kEmitQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
+      else if (mode == kEmitQuads) k_faces<unsigned long long, kEmitQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
+      else if (id_bytes == 4) k_faces<uint32_t, kEmitTrisFixed><<<blocks, kFaceThreads, 0, h->stream>>>(a);
+      else k_faces<unsigned long long, kEmitTrisFixed><<<blocks, kFaceThreads, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     }

@@ -78,10 +78,14 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_excl[3];
 
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // persistent CTAs: few enough tiles are in flight that a look-back finds a finished prefix within a few
+  // descriptors (a grid of one CTA per tile kept ~1200 tiles in flight and walked through all of them)
+  while (true) {
   if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const int tile = (int)s_tile;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (tile >= (int)a.n_tiles) break;
 
   const size_t g0 = (size_t)tile * kScanTile + (size_t)threadIdx.x * kScanPerThread;  // within the range
   uint32_t c[kScanPerThread];
@@ -123,30 +127,21 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
     if (i < warp) warp_excl += t;
     block_total += t;
   }
-  const unsigned long long agg[3] = {block_total & 0x1fffffull, (block_total >> 21) & 0x1fffffull, block_total >> 42};
 
-  if (warp == 0) {
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k)
-        st_relaxed(a.status + (size_t)k * a.n_tiles + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | agg[k]);
-    }
-    unsigned long long ex[3] = {0, 0, 0};
+  if (warp < 3) {
+    // warps 0..2 chain one quantity each, concurrently (three look-backs in a row tripled the tile latency)
+    const int k = warp;
+    unsigned long long* st = a.status + (size_t)k * a.n_tiles;
+    const unsigned long long aggk = (block_total >> (21 * k)) & 0x1fffffull;
+    if (lane == 0) st_relaxed(st + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | aggk);
+    unsigned long long ex = 0;
     if (tile > 0) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) ex[k] = lookback(a.status + (size_t)k * a.n_tiles, tile, lane);
-      if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) st_relaxed(a.status + (size_t)k * a.n_tiles + tile, kFlagPrefix | (ex[k] + agg[k]));
-      }
+      ex = lookback(st, tile, lane);
+      if (lane == 0) st_relaxed(st + tile, kFlagPrefix | (ex + aggk));
     }
     if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) s_excl[k] = ex[k];
-      if ((size_t)(tile + 1) * kScanTile >= a.n) {  // last tile: grand totals
-#pragma unroll
-        for (int k = 0; k < 3; ++k) a.totals[k] = ex[k] + agg[k];
-      }
+      s_excl[k] = ex;
+      if ((size_t)(tile + 1) * kScanTile >= a.n) a.totals[k] = ex + aggk;  // last tile: grand totals
     }
   }
   __syncthreads();
@@ -171,6 +166,8 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
         reinterpret_cast<uint4*>(a.cofs + e)[v4] = ok;
       }
     }
+  }
+  __syncthreads();  // s_tile / s_warp / s_excl are reused by the next tile
   }
 }
 

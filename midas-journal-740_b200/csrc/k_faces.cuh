@@ -32,15 +32,15 @@ struct FaceArgs {
   int pix_bytes;
 };
 
-template <typename IdT>
+template <typename IdT, int MODE>
 __device__ __forceinline__ void write_cell(const FaceArgs& a, size_t fidx, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
-  if (a.mode == kEmitScratchQuads) {
+  if (MODE == kEmitScratchQuads) {
     reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4(q0, q1, q2, q3);
     return;
   }
   const IdT v0 = (IdT)(q0 + a.id_delta), v1 = (IdT)(q1 + a.id_delta), v2 = (IdT)(q2 + a.id_delta), v3 = (IdT)(q3 + a.id_delta);
   IdT* c = reinterpret_cast<IdT*>(a.cells);
-  if (a.mode == kEmitQuads) {
+  if (MODE == kEmitQuads) {
     c += fidx * 4;
     if (sizeof(IdT) == 4) {
       *reinterpret_cast<uint4*>(c) = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, (uint32_t)v3);
@@ -55,9 +55,10 @@ __device__ __forceinline__ void write_cell(const FaceArgs& a, size_t fidx, uint3
   }
 }
 
+template <int MODE>
 __device__ __forceinline__ void write_celldata(const FaceArgs& a, size_t fidx, size_t voxel) {
   const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vol) + voxel * a.pix_bytes;
-  const bool two = (a.mode != kEmitQuads);
+  const bool two = (MODE != kEmitQuads);
   unsigned char* dst = reinterpret_cast<unsigned char*>(a.celldata) + (two ? 2 * fidx : fidx) * a.pix_bytes;
   for (int bb = 0; bb < a.pix_bytes; ++bb) {
     const unsigned char v = src[bb];
@@ -66,88 +67,136 @@ __device__ __forceinline__ void write_celldata(const FaceArgs& a, size_t fidx, s
   }
 }
 
-template <typename IdT>
-__global__ void __launch_bounds__(256) k_faces(const FaceArgs a) {
+constexpr int kFaceThreads = 256;
+
+// per-word context a warp shares through shared memory: 5 x uint4
+//   [0] A[oz][oy]   active masks of the 4 corner words       [1] C[oz][oy]  their slot bases
+//   [2] Cn[oz][oy]  slot bases of the corner words at w+1     [3] F0..F3     [4] F4, F5, face base, -
+struct FaceSmem {
+  uint4 ctx[kFaceThreads / 32][32][5];
+  unsigned long long vox0[kFaceThreads / 32][32];  // index of the word's voxel 0 in the volume (cell data)
+  uint16_t queue[kFaceThreads / 32][1024];         // (lane << 5) | bit of every surface voxel of the warp's words
+};
+
+// One thread per 32-voxel word computes the face masks; the surface voxels of a warp's 32 words are then
+// compacted into a queue and handled one per lane, so a word with ten surface voxels does not stall the 31
+// lanes whose words have none.
+template <typename IdT, int MODE>
+__global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
+  __shared__ FaceSmem sm;
   const Grid& g = a.g;
-  // one thread per voxel word of the padded bitmask layout, own slices only
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t slice_words = (size_t)g.Y * g.Wp;
-  const size_t n = slice_words * (size_t)(a.z_end - a.z_begin);
-  const size_t gi = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gi >= n) return;
-  const int zl = a.z_begin + (int)(gi / slice_words);
-  const int rem = (int)(gi - (size_t)(zl - a.z_begin) * slice_words);
-  const int y = rem / g.Wp, w = rem - y * g.Wp;
-  if (w >= g.Wx) return;
+  // grid: x = 32-word segments of a row, y = groups of 8 rows (one row per warp), z = own slices
+  const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kFaceThreads / 32) + warp, zl = a.z_begin + blockIdx.z;
 
   // ---- face masks of the word (txx:164-173; clamped neighbours: no face on the image border) --------------
-  const int zgl = zl + g.zg0;
-  const int ym = max(y - 1, 0), yp = min(y + 1, g.Y - 1);
-  const int zm = min(max(max(zgl - 1, 0) - g.zg0, 0), g.Zl - 1), zp = max(min(min(zgl + 1, g.Zg - 1) - g.zg0, g.Zl - 1), 0);
-  const uint32_t* __restrict__ row = a.bits + (size_t)zl * slice_words + (size_t)y * g.Wp;
-  const uint32_t c0 = __ldg(row + w);
-  const uint32_t XB = g.X & 31;
-  const uint32_t vc = (w == g.Wx - 1 && XB) ? ((1u << XB) - 1u) : ~0u;
-  const uint32_t c = c0 & vc;
-  if (c == 0) return;  // no inside voxel, no face
-  const uint32_t prev = (w == 0) ? (c0 << 31) : __ldg(row + w - 1);
-  const uint32_t next = (w == g.Wx - 1) ? (c0 >> 31) : __ldg(row + w + 1);
-  uint32_t F[6];
-  F[0] = c & ~__funnelshift_l(prev, c0, 1);
-  F[1] = c & ~__ldg(a.bits + (size_t)zl * slice_words + (size_t)ym * g.Wp + w);
-  F[2] = c & ~__funnelshift_r(c0, next, 1);
-  F[3] = c & ~__ldg(a.bits + (size_t)zl * slice_words + (size_t)yp * g.Wp + w);
-  F[4] = c & ~__ldg(a.bits + (size_t)zm * slice_words + (size_t)y * g.Wp + w);
-  F[5] = c & ~__ldg(a.bits + (size_t)zp * slice_words + (size_t)y * g.Wp + w);
-  uint32_t U = F[0] | F[1] | F[2] | F[3] | F[4] | F[5];
-  if (U == 0) return;
-
-  // ---- the corner words around this voxel word ------------------------------------------------------------
-  const size_t plane = (size_t)a.EY * a.EW;
-  const size_t e00 = ((size_t)zl * a.EY + y) * a.EW + w;  // corner word (w, y, z)
-  uint32_t A[2][2], C[2][2], Cn[2][2];                     // [oz][oy]: active mask, slot base, slot base of word w+1
-#pragma unroll
-  for (int oz = 0; oz < 2; ++oz)
-#pragma unroll
-    for (int oy = 0; oy < 2; ++oy) {
-      const size_t e = e00 + oz * plane + (size_t)oy * a.EW;
-      A[oz][oy] = __ldg(a.act + e);
-      C[oz][oy] = __ldg(a.cofs + e);
-      Cn[oz][oy] = __ldg(a.cofs + e + 1);  // EW >= Wc + ... : entry w+1 always exists (padded rows)
+  uint32_t F[6] = {0, 0, 0, 0, 0, 0};
+  {
+    if (w < g.Wx && y < g.Y) {
+      const uint32_t* __restrict__ row = a.bits + ((size_t)zl * g.Y + y) * g.Wp + w;
+      const uint32_t c0 = __ldg(row);
+      const uint32_t XB = g.X & 31;
+      const uint32_t vc = (w == g.Wx - 1 && XB) ? ((1u << XB) - 1u) : ~0u;
+      const uint32_t c = c0 & vc;
+      if (c) {
+        // neighbour rows / slices as signed word offsets from `row` (0 = clamped onto the row itself)
+        const int zgl = zl + g.zg0;
+        const int sw = g.Y * g.Wp;  // words per slice (< 2^31: checked by cub_count)
+        const int dym = (y > 0) ? -g.Wp : 0, dyp = (y < g.Y - 1) ? g.Wp : 0;
+        const int dzm = (zgl > 0 && zl > 0) ? -sw : 0, dzp = (zgl < g.Zg - 1 && zl < g.Zl - 1) ? sw : 0;
+        const uint32_t prev = (w == 0) ? (c0 << 31) : __ldg(row - 1);
+        const uint32_t next = (w == g.Wx - 1) ? (c0 >> 31) : __ldg(row + 1);
+        F[0] = c & ~__funnelshift_l(prev, c0, 1);
+        F[1] = c & ~__ldg(row + dym);
+        F[2] = c & ~__funnelshift_r(c0, next, 1);
+        F[3] = c & ~__ldg(row + dyp);
+        F[4] = c & ~__ldg(row + dzm);
+        F[5] = c & ~__ldg(row + dzp);
+      }
     }
-  size_t fi = (size_t)(__ldg(a.fofs + e00) - a.ghost_f);
+  }
+  uint32_t U = F[0] | F[1] | F[2] | F[3] | F[4] | F[5];
+  const uint32_t nvox = __popc(U);
+  uint32_t incl = nvox;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += v;
+  }
+  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+  if (total == 0) return;  // most warps: no surface voxel in 1024 voxels
 
-  while (U) {
-    const int b = __ffs(U) - 1;
-    U &= U - 1;
+  if (U) {
+    // ---- context of the word: the corner words around it ------------------------------------------------
+    const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
+    const size_t e00 = ((size_t)zl * a.EY + y) * a.EW + w;  // corner word (w, y, z)
+    const uint32_t* __restrict__ ap = a.act + e00;
+    const uint32_t* __restrict__ cp = a.cofs + e00;
+    uint32_t A[4], C[4], Cn[4];                              // index oz*2+oy
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int d = (k >> 1) * plane + (k & 1) * a.EW;
+      A[k] = __ldg(ap + d);
+      C[k] = __ldg(cp + d);
+      Cn[k] = __ldg(cp + d + 1);
+    }
+    uint4* cx = sm.ctx[warp][lane];
+    cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
+    cx[1] = make_uint4(C[0], C[1], C[2], C[3]);
+    cx[2] = make_uint4(Cn[0], Cn[1], Cn[2], Cn[3]);
+    cx[3] = make_uint4(F[0], F[1], F[2], F[3]);
+    cx[4] = make_uint4(F[4], F[5], __ldg(a.fofs + e00) - a.ghost_f, 0u);
+    if (a.celldata) sm.vox0[warp][lane] = ((unsigned long long)zl * g.Y + y) * g.X + (unsigned long long)w * 32;
+    uint32_t pos = incl - nvox;
+    uint16_t* q = sm.queue[warp];
+    const uint32_t tag = (uint32_t)lane << 5;
+    while (U) {
+      const int b = __ffs(U) - 1;
+      U &= U - 1;
+      q[pos++] = (uint16_t)(tag | (uint32_t)b);
+    }
+  }
+  __syncwarp();
+
+  for (uint32_t s = lane; s < total; s += 32) {
+    const uint32_t it = sm.queue[warp][s];
+    const uint32_t src = it >> 5, b = it & 31u;
+    const uint4* cx = sm.ctx[warp][src];
+    const uint4 A4 = cx[0], C4 = cx[1], N4 = cx[2], Fa = cx[3], Fb = cx[4];
+    const uint32_t A[4] = {A4.x, A4.y, A4.z, A4.w}, C[4] = {C4.x, C4.y, C4.z, C4.w}, Cn[4] = {N4.x, N4.y, N4.z, N4.w};
+    const uint32_t Fm[6] = {Fa.x, Fa.y, Fa.z, Fa.w, Fb.x, Fb.y};
     const uint32_t bit = 1u << b, below = bit - 1u;
-    // vertex ids of the 8 corners of voxel b; local l -> (ox, oy, oz) as in txx:236-254
+    // index of the voxel's first face: faces of the voxels before it in the word
+    size_t fi = Fb.z;
+#pragma unroll
+    for (int f = 0; f < 6; ++f) fi += __popc(Fm[f] & below);
+    // slots of the 8 corners of voxel b; local l -> (ox, oy, oz) as in txx:236-254
     uint32_t vid[8];
 #pragma unroll
-    for (int oz = 0; oz < 2; ++oz)
-#pragma unroll
-      for (int oy = 0; oy < 2; ++oy) {
-        const uint32_t s0 = C[oz][oy] + __popc(A[oz][oy] & below);                        // corner x
-        const uint32_t s1 = (b == 31) ? Cn[oz][oy] : s0 + ((A[oz][oy] >> b) & 1u);        // corner x+1
-        const int l0 = oz * 4 + (oy ? 3 : 0), l1 = oz * 4 + (oy ? 2 : 1);
-        vid[l0] = s0;
-        vid[l1] = s1;
-      }
-    // which corners are needed (vertexHasQuad): local l touches the faces in its three directions
-    const bool f0 = F[0] & bit, f1 = F[1] & bit, f2 = F[2] & bit, f3 = F[3] & bit, f4 = F[4] & bit, f5 = F[5] & bit;
+    for (int k = 0; k < 4; ++k) {
+      const int oz = k >> 1, oy = k & 1;
+      const uint32_t s0 = C[k] + __popc(A[k] & below);                      // corner x
+      const uint32_t s1 = (b == 31) ? Cn[k] : s0 + ((A[k] >> b) & 1u);      // corner x+1
+      vid[oz * 4 + (oy ? 3 : 0)] = s0;
+      vid[oz * 4 + (oy ? 2 : 1)] = s1;
+    }
+    const bool f0 = Fm[0] & bit, f1 = Fm[1] & bit, f2 = Fm[2] & bit, f3 = Fm[3] & bit, f4 = Fm[4] & bit, f5 = Fm[5] & bit;
     if (a.perm) {
+      // only the corners of present faces have a vertex (vertexHasQuad, txx:164-173)
       const bool need[8] = {f0 || f1 || f4, f1 || f2 || f4, f2 || f3 || f4, f0 || f3 || f4,
                             f0 || f1 || f5, f1 || f2 || f5, f2 || f3 || f5, f0 || f3 || f5};
 #pragma unroll
       for (int l = 0; l < 8; ++l)
         if (need[l]) vid[l] = __ldg(a.perm + vid[l]);
     }
-    const size_t voxel = ((size_t)zl * g.Y + y) * g.X + (size_t)w * 32 + b;
-    if (f0) { write_cell<IdT>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
-    if (f1) { write_cell<IdT>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
-    if (f2) { write_cell<IdT>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
-    if (f3) { write_cell<IdT>(a, fi, vid[2], vid[3], vid[7], vid[6]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
-    if (f4) { write_cell<IdT>(a, fi, vid[0], vid[3], vid[2], vid[1]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
-    if (f5) { write_cell<IdT>(a, fi, vid[4], vid[5], vid[6], vid[7]); if (a.celldata) write_celldata(a, fi, voxel); ++fi; }
+    const size_t voxel = a.celldata ? (size_t)(sm.vox0[warp][src] + b) : 0;
+    if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f3) { write_cell<IdT, MODE>(a, fi, vid[2], vid[3], vid[7], vid[6]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f4) { write_cell<IdT, MODE>(a, fi, vid[0], vid[3], vid[2], vid[1]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f5) { write_cell<IdT, MODE>(a, fi, vid[4], vid[5], vid[6], vid[7]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
   }
 }
 
