@@ -216,13 +216,9 @@ def main():
     h = capi.Handle(local_rank, stream.cuda_stream)
 
     S = args.size
-    if args.scaling == "weak":
-        image_nz, own0, own1 = S * N, rank * S, (rank + 1) * S
-    else:
-        image_nz = S
-        own0, own1 = (S * rank) // N, (S * (rank + 1)) // N
-    halo = 2
-    lo, hi = max(0, own0 - halo), min(image_nz, own1 + halo)
+    image_nz = S * N if args.scaling == "weak" else S
+    slab = P.slabs.plan_slabs(image_nz, N, halo=2)[rank]
+    own0, own1, lo, hi = slab.own_z0, slab.own_z1, slab.local_z0, slab.local_z1
     kind = FIELD_KIND[args.field]
     p0, p1 = (args.period, 1.0) if args.field == "gyroid" else ((48.0, 1.0) if args.field == "blobs" else (0.0, 0.0))
     h.generate(kind, (S, S, hi - lo), (S, S, image_nz), lo, p0, p1)
@@ -232,21 +228,18 @@ def main():
     prm = capi.default_params()
     prm.iso_value, prm.generate_triangles, prm.project_vertices = iso, 0, 0
 
-    counts_dev = torch.zeros(2, dtype=torch.int64, device=dev)
-    gathered = torch.zeros(2 * N, dtype=torch.int64, device=dev)
+    last_counts = [None]
 
-    def step(params=prm):
-        n_pts, n_quads = h.count(params)
-        if N > 1:
-            counts_dev.copy_(torch.tensor([n_pts, n_quads], dtype=torch.int64), non_blocking=False)
-            dist.all_gather_into_tensor(gathered, counts_dev)
-            g = gathered.cpu().view(N, 2)
-            h.set_id_base(int(g[:rank, 0].sum()), int(g[:rank, 1].sum()))
-            tot = (int(g[:, 0].sum()), int(g[:, 1].sum()))
-        else:
-            tot = (n_pts, n_quads)
-        h.emit(4)
-        return n_pts, n_quads, tot
+    def step(params=prm, handle=None):
+        hh = handle or h
+        n_pts, n_quads = hh.count(params)
+        counts = P.slabs.all_gather_counts(n_pts, n_quads, dev)   # the only exchange of the data path
+        last_counts[0] = counts
+        cells_per_quad = 2 if params.generate_triangles else 1
+        pbase, cbase = P.slabs.exclusive_bases(counts, rank)
+        hh.set_id_base(pbase, cbase * cells_per_quad)
+        hh.emit(4)
+        return n_pts, n_quads, (sum(c[0] for c in counts), sum(c[1] for c in counts))
 
     def barrier():
         if N > 1:
@@ -287,7 +280,7 @@ def main():
 
     # ---- per-kernel device times (CUDA events inside the library, separate passes) ---------------
     h.enable_timing(True)
-    kt = {"classify": [], "count_scan": [], "emit": []}
+    kt = {"classify": [], "count_scan": [], "scan_only": [], "emit": []}
     for _ in range(max(3, min(args.steps, 10))):
         step()
         t = h.timings()
@@ -343,13 +336,7 @@ def main():
             he.set_volume_ptr(vol_host.data_ptr(), np.float32, (S, S, hi - lo), capi.MEM_HOST)
             if N > 1:
                 he.set_slab(image_nz, lo, own0, own1)
-            a, b = he.count(prm)
-            if N > 1:
-                counts_dev.copy_(torch.tensor([a, b], dtype=torch.int64))
-                dist.all_gather_into_tensor(gathered, counts_dev)
-                g = gathered.cpu().view(N, 2)
-                he.set_id_base(int(g[:rank, 0].sum()), int(g[:rank, 1].sum()))
-            he.emit(4)
+            a, b, _ = step(prm, he)
             he.fetch_into(pts_host.data_ptr(), cells_host.data_ptr())
             return a, b, None
 
@@ -363,9 +350,7 @@ def main():
     # ---- optional: all-gather of the meshes over NVLink (reported separately) -----------
     gather = None
     if args.gather and N > 1:
-        info = h.device_buffers()
-        g = gathered.cpu().view(N, 2)
-        maxp, maxq = int(g[:, 0].max()), int(g[:, 1].max())
+        maxp, maxq = max(c[0] for c in last_counts[0]), max(c[1] for c in last_counts[0])
         # padded all-gather straight from the result buffers (uneven sizes -> pad to the max)
         src_p = torch.zeros(maxp * 3, dtype=torch.float32, device=dev)
         src_c = torch.zeros(maxq * 4, dtype=torch.int32, device=dev)

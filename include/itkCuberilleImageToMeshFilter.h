@@ -1,0 +1,317 @@
+/*=========================================================================
+ * itkCuberilleImageToMeshFilter.h — drop-in replacement of the reference header
+ *   Source/itkCuberilleImageToMeshFilter.h (+ .txx)
+ * whose GenerateData() runs on a B200 through the C-ABI of include/cuberille_c.h.
+ *
+ * Same class name, template parameters, typedefs and public interface as the
+ * reference (h:110-228): SetInput, Set/GetIsoSurfaceValue, Set/GetInterpolator,
+ * GenerateTriangleFaces / ProjectVerticesToIsoSurface with On/Off, the three
+ * projection knobs with their clamp ranges, ProjectVertexMaximumNumberOfSteps,
+ * plus SavePixelAsCellData (BASELINE.json north star; the reference only has
+ * commented SetCellData stubs, txx:314,321,330).  Update() / GetOutput() come from
+ * itk::ImageToMeshFilter as in the reference.  Constructor defaults: txx:31-41.
+ *
+ * This header contains NO algorithm: GenerateData() hands the image buffer to
+ * libcuberille_cuda.so (cub_set_volume / cub_run / cub_fetch) and fills the
+ * itk::Mesh with what comes back, in the reference's point and cell order.
+ * Link with -lcuberille_cuda.  C-ABI errors become itk::ExceptionObject through
+ * itkExceptionMacro, like every other ITK filter failure the reference's driver
+ * catches (Testing/CuberilleTest01.cxx:207-212).
+ *
+ * Differences from the reference, all documented in DESIGN.md §7:
+ *  - TInterpolator must be itk::LinearInterpolateImageFunction<TInputImage>
+ *    (the device kernel implements ITK's trilinear interpolation; another
+ *    interpolator type raises an exception instead of being silently ignored);
+ *  - the image direction must be the identity and the buffered region must start
+ *    at index 0 (exception otherwise);
+ *  - a zero image gradient stops a vertex instead of dividing by zero (txx:452),
+ *    out-of-image interpolation reads are clamped instead of undefined.
+ *=========================================================================*/
+#ifndef __itkCuberilleImageToMeshFilter_h
+#define __itkCuberilleImageToMeshFilter_h
+
+#include <cstdint>
+#include <type_traits>
+#include <vector>
+
+#include "itkMacro.h"
+#include "itkMesh.h"
+#include "itkImageToMeshFilter.h"
+#include "itkCellInterface.h"
+#include "itkTriangleCell.h"
+#include "itkQuadrilateralCell.h"
+#include "itkLinearInterpolateImageFunction.h"
+#include "itkNumericTraits.h"
+
+#include "cuberille_c.h"
+
+namespace itk
+{
+
+namespace cuberille_detail
+{
+template <typename T> struct PixelCode;
+template <> struct PixelCode<unsigned char>  { static const int value = CUB_U8; };
+template <> struct PixelCode<signed char>    { static const int value = CUB_I8; };
+template <> struct PixelCode<char>           { static const int value = std::is_signed<char>::value ? CUB_I8 : CUB_U8; };
+template <> struct PixelCode<unsigned short> { static const int value = CUB_U16; };
+template <> struct PixelCode<short>          { static const int value = CUB_I16; };
+template <> struct PixelCode<unsigned int>   { static const int value = CUB_U32; };
+template <> struct PixelCode<int>            { static const int value = CUB_I32; };
+template <> struct PixelCode<float>          { static const int value = CUB_F32; };
+template <> struct PixelCode<double>         { static const int value = CUB_F64; };
+}
+
+template < class TInputImage, class TOutputMesh, class TInterpolator = itk::LinearInterpolateImageFunction<TInputImage> >
+class ITK_EXPORT CuberilleImageToMeshFilter : public ImageToMeshFilter< TInputImage, TOutputMesh >
+{
+public:
+  /** Standard "Self" typedef. */
+  typedef CuberilleImageToMeshFilter                    Self;
+  typedef ImageToMeshFilter< TInputImage, TOutputMesh > Superclass;
+  typedef SmartPointer<Self>                            Pointer;
+  typedef SmartPointer<const Self>                      ConstPointer;
+
+  itkNewMacro(Self);
+  itkTypeMacro(CuberilleImageToMeshFilter, ImageToMeshFilter);
+
+  /** Same convenience typedefs as the reference (h:126-159). */
+  typedef TOutputMesh                           OutputMeshType;
+  typedef typename OutputMeshType::Pointer      OutputMeshPointer;
+  typedef typename OutputMeshType::MeshTraits   OutputMeshTraits;
+  typedef typename OutputMeshType::PointType    OutputPointType;
+  typedef typename OutputMeshTraits::PixelType  OutputPixelType;
+  typedef typename OutputMeshType::CellTraits   CellTraits;
+  typedef typename OutputMeshType::PointsContainerPointer PointsContainerPointer;
+  typedef typename OutputMeshType::PointsContainer        PointsContainer;
+  typedef typename OutputMeshType::CellsContainerPointer  CellsContainerPointer;
+  typedef typename OutputMeshType::CellsContainer         CellsContainer;
+  typedef typename OutputMeshType::PointIdentifier        PointIdentifier;
+  typedef typename OutputMeshType::CellIdentifier         CellIdentifier;
+  typedef CellInterface<OutputPixelType, CellTraits>      CellInterfaceType;
+  typedef TriangleCell<CellInterfaceType>                 TriangleCellType;
+  typedef typename TriangleCellType::CellAutoPointer      TriangleCellAutoPointer;
+  typedef QuadrilateralCell<CellInterfaceType>            QuadrilateralCellType;
+  typedef typename QuadrilateralCellType::CellAutoPointer QuadrilateralCellAutoPointer;
+
+  typedef TInputImage                               InputImageType;
+  typedef typename InputImageType::Pointer          InputImagePointer;
+  typedef typename InputImageType::ConstPointer     InputImageConstPointer;
+  typedef typename InputImageType::PixelType        InputPixelType;
+  typedef typename InputImageType::SizeType         SizeType;
+  typedef typename InputImageType::SpacingType      SpacingType;
+  typedef typename InputImageType::SpacingValueType SpacingValueType;
+  typedef typename InputImageType::IndexType        IndexType;
+  typedef typename OutputMeshType::PointType        PointType;
+
+  typedef TInterpolator                      InterpolatorType;
+  typedef typename InterpolatorType::Pointer InterpolatorPointer;
+
+  /** Get/set the iso-surface value (h:180-181): pixels >= this value are inside (txx:139-141). */
+  itkGetMacro( IsoSurfaceValue, InputPixelType );
+  itkSetMacro( IsoSurfaceValue, InputPixelType );
+
+  /** Accept the input image (h:184, txx:53-56). */
+  virtual void SetInput( const InputImageType * inputImage )
+    {
+    this->ProcessObject::SetNthInput( 0, const_cast< InputImageType * >( inputImage ) );
+    }
+
+  /** Get/set interpolate function (h:187-188).  Kept for source compatibility; only its TYPE matters. */
+  itkGetObjectMacro( Interpolator, InterpolatorType );
+  itkSetObjectMacro( Interpolator, InterpolatorType );
+
+  /** True = triangle faces, false = quadrilateral faces; default true (h:193-195). */
+  itkGetMacro( GenerateTriangleFaces, bool );
+  itkSetMacro( GenerateTriangleFaces, bool );
+  itkBooleanMacro( GenerateTriangleFaces );
+
+  /** Project the vertices onto the iso-surface; default true (h:199-201). */
+  itkGetMacro( ProjectVerticesToIsoSurface, bool );
+  itkSetMacro( ProjectVerticesToIsoSurface, bool );
+  itkBooleanMacro( ProjectVerticesToIsoSurface );
+
+  /** Store the generating voxel's pixel value as cell data of every cell; default false. */
+  itkGetMacro( SavePixelAsCellData, bool );
+  itkSetMacro( SavePixelAsCellData, bool );
+  itkBooleanMacro( SavePixelAsCellData );
+
+  /** Projection knobs with the reference's clamp ranges (h:209-228). */
+  itkGetMacro( ProjectVertexSurfaceDistanceThreshold, double );
+  itkSetClampMacro( ProjectVertexSurfaceDistanceThreshold, double, 0.0, NumericTraits<InputPixelType>::max() );
+  itkGetMacro( ProjectVertexStepLength, double );
+  itkSetClampMacro( ProjectVertexStepLength, double, 0.0, 100000.0 );
+  itkGetMacro( ProjectVertexStepLengthRelaxationFactor, double );
+  itkSetClampMacro( ProjectVertexStepLengthRelaxationFactor, double, 0.0, 1.0 );
+  itkGetMacro( ProjectVertexMaximumNumberOfSteps, unsigned int );
+  itkSetMacro( ProjectVertexMaximumNumberOfSteps, unsigned int );
+
+  /** CUDA device ordinal used by this filter instance (default 0). */
+  itkGetMacro( Device, int );
+  itkSetMacro( Device, int );
+
+protected:
+  CuberilleImageToMeshFilter()
+    {
+    // txx:31-41
+    this->SetNumberOfRequiredInputs(1);
+    m_IsoSurfaceValue = NumericTraits< InputPixelType >::One;
+    m_GenerateTriangleFaces = true;
+    m_ProjectVerticesToIsoSurface = true;
+    m_SavePixelAsCellData = false;
+    m_ProjectVertexSurfaceDistanceThreshold = 0.5;
+    m_ProjectVertexStepLength = -1.0;
+    m_ProjectVertexStepLengthRelaxationFactor = 0.95;
+    m_ProjectVertexMaximumNumberOfSteps = 50;
+    m_Device = 0;
+    m_Handle = 0;
+    }
+
+  ~CuberilleImageToMeshFilter()
+    {
+    if ( m_Handle ) { cub_destroy( m_Handle ); }
+    }
+
+  void PrintSelf( std::ostream& os, Indent indent ) const
+    {
+    // txx:501-520
+    Superclass::PrintSelf( os, indent );
+    os << indent << "IsoSurfaceValue: "
+       << static_cast< typename NumericTraits<InputPixelType>::PrintType >( m_IsoSurfaceValue ) << std::endl;
+    os << indent << "GenerateTriangleFaces: " << m_GenerateTriangleFaces << std::endl;
+    os << indent << "ProjectVerticesToIsoSurface: " << m_ProjectVerticesToIsoSurface << std::endl;
+    os << indent << "SavePixelAsCellData: " << m_SavePixelAsCellData << std::endl;
+    }
+
+  virtual void GenerateOutputInformation() { } // do nothing (h:236)
+
+  /** The hot path: txx:59-216, executed by libcuberille_cuda.so. */
+  void GenerateData()
+    {
+    if ( !std::is_same< TInterpolator, LinearInterpolateImageFunction<TInputImage> >::value )
+      {
+      itkExceptionMacro( << "the CUDA cuberille path implements itk::LinearInterpolateImageFunction only" );
+      }
+    InputImageConstPointer image = Superclass::GetInput( 0 );
+    typename OutputMeshType::Pointer mesh = Superclass::GetOutput();
+
+    // image geometry (txx:75-79, 266-270)
+    const typename InputImageType::RegionType region = image->GetBufferedRegion();
+    uint64_t dims[3];
+    double spacing[3], origin[3], direction[9];
+    double maxSpacing = 0.0;
+    for ( unsigned int i = 0; i < 3; i++ )
+      {
+      if ( region.GetIndex()[i] != 0 )
+        {
+        itkExceptionMacro( << "the buffered region must start at index 0" );
+        }
+      dims[i] = region.GetSize()[i];
+      spacing[i] = image->GetSpacing()[i];
+      origin[i] = image->GetOrigin()[i];
+      for ( unsigned int j = 0; j < 3; j++ ) { direction[3*i + j] = image->GetDirection()[i][j]; }
+      maxSpacing = ( spacing[i] > maxSpacing ) ? spacing[i] : maxSpacing;
+      }
+    // sticky default step length (txx:82-85)
+    if ( m_ProjectVertexStepLength < 0.0 )
+      {
+      m_ProjectVertexStepLength = maxSpacing * 0.25;
+      }
+
+    if ( !m_Handle )
+      {
+      if ( cub_create( m_Device, 0, &m_Handle ) != CUB_OK )
+        {
+        m_Handle = 0;
+        itkExceptionMacro( << "cub_create failed: no usable CUDA device " << m_Device << " (there is no CPU fallback)" );
+        }
+      }
+    this->Check( cub_set_volume( m_Handle, image->GetBufferPointer(),
+                                 cuberille_detail::PixelCode<InputPixelType>::value,
+                                 dims, spacing, origin, direction, CUB_MEM_HOST ) );
+    cub_params params;
+    cub_default_params( &params );
+    params.iso_value = static_cast<double>( m_IsoSurfaceValue );
+    params.generate_triangles = m_GenerateTriangleFaces ? 1 : 0;
+    params.project_vertices = m_ProjectVerticesToIsoSurface ? 1 : 0;
+    params.save_pixel_as_cell_data = m_SavePixelAsCellData ? 1 : 0;
+    params.surface_distance_threshold = m_ProjectVertexSurfaceDistanceThreshold;
+    params.step_length = m_ProjectVertexStepLength;
+    params.step_relaxation = m_ProjectVertexStepLengthRelaxationFactor;
+    params.max_steps = m_ProjectVertexMaximumNumberOfSteps;
+
+    uint64_t numberOfPoints = 0, numberOfCells = 0;
+    this->Check( cub_run( m_Handle, &params, 8, &numberOfPoints, &numberOfCells ) );  // PointIdentifier: unsigned long
+
+    const unsigned int verticesPerCell = m_GenerateTriangleFaces ? 3 : 4;
+    std::vector<float> points( 3 * numberOfPoints );
+    std::vector<uint64_t> cells( verticesPerCell * numberOfCells );
+    std::vector<InputPixelType> cellData( m_SavePixelAsCellData ? numberOfCells : 0 );
+    this->Check( cub_fetch( m_Handle, points.empty() ? 0 : &points[0], cells.empty() ? 0 : &cells[0],
+                            cellData.empty() ? 0 : &cellData[0], CUB_MEM_HOST ) );
+
+    // mesh->GetPoints()->InsertElement( id, vertex )   (txx:275)
+    mesh->GetPoints()->Reserve( numberOfPoints );
+    for ( uint64_t id = 0; id < numberOfPoints; id++ )
+      {
+      PointType p;
+      p[0] = points[3*id]; p[1] = points[3*id + 1]; p[2] = points[3*id + 2];
+      mesh->GetPoints()->SetElement( static_cast<PointIdentifier>( id ), p );
+      }
+    // mesh->SetCell( id, cell )   (txx:310-329): one heap cell per face, as ITK meshes require
+    for ( uint64_t id = 0; id < numberOfCells; id++ )
+      {
+      PointIdentifier ids[4];
+      for ( unsigned int k = 0; k < verticesPerCell; k++ )
+        {
+        ids[k] = static_cast<PointIdentifier>( cells[verticesPerCell*id + k] );
+        }
+      if ( m_GenerateTriangleFaces )
+        {
+        TriangleCellAutoPointer tri;
+        tri.TakeOwnership( new TriangleCellType );
+        tri->SetPointIds( ids );
+        mesh->SetCell( static_cast<CellIdentifier>( id ), tri );
+        }
+      else
+        {
+        QuadrilateralCellAutoPointer quad;
+        quad.TakeOwnership( new QuadrilateralCellType );
+        quad->SetPointIds( ids );
+        mesh->SetCell( static_cast<CellIdentifier>( id ), quad );
+        }
+      if ( m_SavePixelAsCellData )
+        {
+        mesh->SetCellData( static_cast<CellIdentifier>( id ), static_cast<OutputPixelType>( cellData[id] ) );
+        }
+      }
+    }
+
+private:
+  CuberilleImageToMeshFilter(const Self&); //purposely not implemented
+  void operator=(const Self&);             //purposely not implemented
+
+  void Check( int status )
+    {
+    if ( status != CUB_OK )
+      {
+      itkExceptionMacro( << "cuberille C-ABI error " << status << ": " << cub_last_error( m_Handle ) );
+      }
+    }
+
+  InputPixelType      m_IsoSurfaceValue;
+  InterpolatorPointer m_Interpolator;
+  bool                m_GenerateTriangleFaces;
+  bool                m_ProjectVerticesToIsoSurface;
+  bool                m_SavePixelAsCellData;
+  double              m_ProjectVertexSurfaceDistanceThreshold;
+  double              m_ProjectVertexStepLength;
+  double              m_ProjectVertexStepLengthRelaxationFactor;
+  unsigned int        m_ProjectVertexMaximumNumberOfSteps;
+  int                 m_Device;
+  cub_handle          m_Handle;
+};
+
+} // end namespace itk
+
+#endif

@@ -1,0 +1,55 @@
+"""z-slab decomposition of the hot path across ranks.
+
+The reference's GenerateData is one raster loop (txx:136-206); concatenating contiguous z-slabs keeps
+its cell order and its first-touch vertex order.  Each rank runs the same kernels on its slab (with a
+halo) and the ONLY exchange of the data path is an all-gather of two integers per rank: the exclusive
+scan of (points, cells) counts gives the global id bases.  Host logic only - works with any
+torch.distributed backend (nccl on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class Slab:
+    rank: int
+    image_nz: int
+    own_z0: int      # global half-open range of slices whose voxels this rank emits
+    own_z1: int
+    local_z0: int    # global half-open range of slices the rank holds (own range + halo, clipped to the image)
+    local_z1: int
+
+
+def plan_slabs(image_nz: int, world: int, halo: int = 2) -> list[Slab]:
+    """Contiguous, near-equal z-slabs; `halo` >= 2 (classification + first-touch ownership of the shared
+    corner plane); use >= 8 when vertices are projected (they travel up to step/(1-relax) voxels)."""
+    if halo < 2:
+        raise ValueError("the halo must be at least 2 slices")
+    if world < 1 or image_nz < world:
+        raise ValueError("need at least one slice per rank")
+    out = []
+    for r in range(world):
+        z0, z1 = (image_nz * r) // world, (image_nz * (r + 1)) // world
+        out.append(Slab(r, image_nz, z0, z1, max(0, z0 - halo), min(image_nz, z1 + halo)))
+    return out
+
+
+def exclusive_bases(counts: list[tuple[int, int]], rank: int) -> tuple[int, int]:
+    """(point id base, cell id base) of `rank` from every rank's (points, cells)."""
+    return sum(c[0] for c in counts[:rank]), sum(c[1] for c in counts[:rank])
+
+
+def all_gather_counts(n_points: int, n_cells: int, device=None) -> list[tuple[int, int]]:
+    """All-gather of the per-rank (points, cells) counts: NCCL has no exclusive scan, so every rank gathers
+    the 2 x world integers and sums its prefix locally.  Single process: no communication."""
+    import torch
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return [(int(n_points), int(n_cells))]
+    world = dist.get_world_size()
+    mine = torch.tensor([n_points, n_cells], dtype=torch.int64, device=device)
+    out = torch.empty(2 * world, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(out, mine)
+    flat = out.cpu().tolist()
+    return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]

@@ -67,6 +67,9 @@ struct orc_mesh {
   int verts_per_cell = 4;
   int pixel_bytes = 1;
   double step_length_used = 0.0;
+  // number of points / cells that exist when the raster loop enters slice z (size nz + 1): what a z-slab
+  // decomposition must reproduce with its exclusive scan of per-slab counts
+  std::vector<uint64_t> points_before_slice, cells_before_slice;
 };
 
 }  // extern "C"
@@ -268,6 +271,11 @@ struct Runner {
   T iso;
   double step0;
 
+  void mark_slice() {
+    mesh->points_before_slice.push_back(mesh->points.size() / 3);
+    mesh->cells_before_slice.push_back(mesh->cells.size() / (size_t)mesh->verts_per_cell);
+  }
+
   void add_vertex(int64_t cx, int64_t cy, int64_t cz) {  // txx:257-276
     float v[3];
     corner_position(vol.g, cx, cy, cz, v);
@@ -333,7 +341,8 @@ struct Runner {
     bool faceHasQuad[6], vertexHasQuad[8];
     uint64_t v[8], f[4];
     const Geometry& g = vol.g;
-    for (int64_t z = 0; z < g.nz; ++z)
+    for (int64_t z = 0; z < g.nz; ++z) {
+      mark_slice();
       for (int64_t y = 0; y < g.ny; ++y)
         for (int64_t x = 0; x < g.nx; ++x) {
           const T center = vol.data[(z * g.ny + y) * g.nx + x];
@@ -367,6 +376,8 @@ struct Runner {
             }
           }
         }
+    }
+    mark_slice();
   }
 
   // ---- mode CLOSED_FORM: ownership by minimal raster*8+local key -----------
@@ -379,7 +390,8 @@ struct Runner {
     uint64_t nextVertexId = 0;
     bool faceHasQuad[6], vertexHasQuad[8];
     uint64_t f[4];
-    for (int64_t z = 0; z < g.nz; ++z)
+    for (int64_t z = 0; z < g.nz; ++z) {
+      mark_slice();
       for (int64_t y = 0; y < g.ny; ++y)
         for (int64_t x = 0; x < g.nx; ++x) {
           const T center = vol.data[(z * g.ny + y) * g.nx + x];
@@ -403,6 +415,8 @@ struct Runner {
             add_quad_face(f, center);
           }
         }
+    }
+    mark_slice();
   }
 };
 
@@ -503,6 +517,9 @@ const uint64_t* orc_cells(const orc_mesh* m) { return m->cells.data(); }
 const void* orc_cell_data(const orc_mesh* m) { return m->celldata.data(); }
 uint64_t orc_cell_data_bytes(const orc_mesh* m) { return m->celldata.size(); }
 double orc_step_length_used(const orc_mesh* m) { return m->step_length_used; }
+// points / cells that exist when the loop enters slice z, z = 0..nz (nz + 1 values each)
+const uint64_t* orc_points_before_slice(const orc_mesh* m) { return m->points_before_slice.data(); }
+const uint64_t* orc_cells_before_slice(const orc_mesh* m) { return m->cells_before_slice.data(); }
 void orc_free(orc_mesh* m) { delete m; }
 
 // inside bitmask, 1 bit per voxel, rows padded to words_per_row 32-bit words,

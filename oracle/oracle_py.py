@@ -62,7 +62,8 @@ def lib() -> C.CDLL:
         for name, rt in [("orc_num_points", C.c_uint64), ("orc_num_cells", C.c_uint64),
                          ("orc_verts_per_cell", C.c_int), ("orc_points", C.c_void_p),
                          ("orc_cells", C.c_void_p), ("orc_cell_data", C.c_void_p),
-                         ("orc_cell_data_bytes", C.c_uint64), ("orc_step_length_used", C.c_double)]:
+                         ("orc_cell_data_bytes", C.c_uint64), ("orc_step_length_used", C.c_double),
+                         ("orc_points_before_slice", C.c_void_p), ("orc_cells_before_slice", C.c_void_p)]:
             getattr(L, name).restype = rt
             getattr(L, name).argtypes = [C.c_void_p]
         L.orc_free.restype = None
@@ -85,6 +86,8 @@ class Mesh:
     cells: np.ndarray       # (m, 3|4) uint64
     cell_data: np.ndarray | None
     step_length_used: float
+    points_before_slice: np.ndarray | None = None   # (nz + 1,) points that exist when the loop enters slice z
+    cells_before_slice: np.ndarray | None = None
 
 
 def _geom(vol: np.ndarray, spacing, origin):
@@ -123,7 +126,12 @@ def cuberille(vol: np.ndarray, iso, *, triangles=True, project=True, cell_data=F
             if m:
                 assert L.orc_cell_data_bytes(h) == cd.nbytes
                 C.memmove(cd.ctypes.data, L.orc_cell_data(h), cd.nbytes)
-        return Mesh(pts, cells, cd, L.orc_step_length_used(h))
+        nz = vol.shape[0]
+        pb = np.empty(nz + 1, np.uint64)
+        cb = np.empty(nz + 1, np.uint64)
+        C.memmove(pb.ctypes.data, L.orc_points_before_slice(h), pb.nbytes)
+        C.memmove(cb.ctypes.data, L.orc_cells_before_slice(h), cb.nbytes)
+        return Mesh(pts, cells, cd, L.orc_step_length_used(h), pb, cb)
     finally:
         L.orc_free(h)
 
