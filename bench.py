@@ -350,6 +350,7 @@ def main():
     # ---- optional: all-gather of the meshes over NVLink (reported separately) -----------
     gather = None
     if args.gather and N > 1:
+        step(prm)  # the handle holds the headline mesh again (quads), whatever the extras ran last
         maxp, maxq = max(c[0] for c in last_counts[0]), max(c[1] for c in last_counts[0])
         # padded all-gather straight from the result buffers (uneven sizes -> pad to the max)
         src_p = torch.zeros(maxp * 3, dtype=torch.float32, device=dev)
