@@ -212,7 +212,11 @@ def main():
 
     P = importlib.import_module("midas-journal-740_b200")
     capi = P.capi
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: torch's default stream has handle 0, which the C-ABI reads as "create your
+    # own stream" - and then torch events would not bracket the library's work
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
     h = capi.Handle(local_rank, stream.cuda_stream)
 
     S = args.size

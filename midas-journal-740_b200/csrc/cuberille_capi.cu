@@ -123,6 +123,9 @@ struct cub_handle_s {
 
   bool timing = false;
   cudaEvent_t ev[10] = {};
+  cudaStream_t aux = nullptr;          // second stream: issue-bound sweeps run beside the HBM-bound classify
+  cudaEvent_t chunk_ev[16] = {};       // per z-chunk "classified" events
+  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
 };
@@ -218,23 +221,24 @@ struct Timer {
   }
 };
 
+// K1 on the local slices [z0, z1) (rows are independent), on `stream`, with at most ctas_per_sm resident CTAs
 template <typename T>
-void launch_classify(cub_handle h) {
-  const Grid& g = h->g;
+void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas_per_sm) {
+  Grid g = h->g;
   const unsigned groups = (unsigned)((g.Wx + kWordsPerTask - 1) / kWordsPerTask);
-  const unsigned long long rows = (unsigned long long)g.Y * g.Zl;
+  const unsigned long long rows = (unsigned long long)g.Y * (z1 - z0);
   const unsigned tasks = (unsigned)(rows * groups);  // dims < 2^31 and cub_count checks rows*groups < 2^32
   unsigned long long blocks = ((unsigned long long)tasks + 7) / 8;
-  const unsigned long long max_blocks = (unsigned long long)kNumSMs * 8 * 4;  // 8 resident CTAs/SM, a few waves
+  const unsigned long long max_blocks = (unsigned long long)kNumSMs * ctas_per_sm;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   const bool full = (g.X % 32 == 0) && (g.Wx % kWordsPerTask == 0);
+  const T* vol = static_cast<const T*>(h->d_vol) + (size_t)z0 * g.Y * g.X;
+  uint32_t* bits = h->bits.p + (size_t)z0 * g.Y * g.Wp;
   if (full)
-    k_classify<T, true><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
-                                                                 (T)h->params.iso_value, tasks, groups);
+    k_classify<T, true><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
   else
-    k_classify<T, false><<<(unsigned)blocks, 256, 0, h->stream>>>(static_cast<const T*>(h->d_vol), h->bits.p, g,
-                                                                  (T)h->params.iso_value, tasks, groups);
+    k_classify<T, false><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
   h->launches++;
 }
 
@@ -320,6 +324,10 @@ int cub_create(int device, void* stream, cub_handle* out) {
             cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost(&h->h_totals, 8 * sizeof(unsigned long long)) == cudaSuccess;
   for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
+  ok = ok && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
   cub_default_params(&h->params);
   *out = h;
@@ -336,6 +344,10 @@ int cub_destroy(cub_handle h) {
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
   for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  for (int i = 0; i < 16; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
+  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
+  if (h->join_ev) cudaEventDestroy(h->join_ev);
+  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return CUB_OK;
@@ -454,31 +466,56 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
 
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
 
-  // K1
-  {
-    Timer t(h, 0);
-    DISPATCH_PIXEL(h->dtype, launch_classify<T>(h));
-    CU_TRY(h, cudaGetLastError());
-    t.stop();
-  }
-  // K2: scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
+  // K2 scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
   const size_t e_begin = (size_t)h->owner_z_min * plane_entries;
   const size_t n_scan = (size_t)(h->zs1 + 1 - h->owner_z_min) * plane_entries;
   const size_t n_tiles = (n_scan + kScanTile - 1) / kScanTile;
   CUB_TRY(ensure(h, h->status, 3 * n_tiles));
-  {
-    Timer t(h, 1);
-    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+  SweepArgs ca{};
+  ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
+  ca.cnt = h->cnt.p; ca.act = h->act.p;
+  const int n_chunks = h->timing ? 1 : std::max(1, std::min(std::min(tuning_knob("CUB_CHUNKS", 1), 16), (h->zs1 - h->owner_z_min) / 64));
+  if (n_chunks == 1) {
+    // serial: K1 then K2a on the handle's stream (also the per-kernel timing path)
     {
-      // K2a: per-entry counts + active-corner masks (z-sweep over the scan range)
-      SweepArgs a{};
-      a.bits = h->bits.p; a.g = g; a.Wc = Wc; a.EY = h->EY; a.EW = h->EW;
-      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-      a.cnt = h->cnt.p; a.act = h->act.p;
-      CU_TRY(h, dispatch_sweep<MODE_COUNT>(a, h->stream));
+      Timer t(h, 0);
+      DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, 0, g.Zl, h->stream, 32));
+      CU_TRY(h, cudaGetLastError());
+      t.stop();
+    }
+    if (h->timing) cudaEventRecord(h->ev[0], h->stream);
+    ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
+    CU_TRY(h, dispatch_sweep<MODE_COUNT>(ca, h->stream));
+    h->launches++;
+  } else {
+    // (opt-in, CUB_CHUNKS > 1; r1 measurement: no gain yet - the sweep's 80 registers leave room for one of its
+    //  CTAs next to the classify CTAs)
+    // z-chunk pipeline: the HBM-bound classify of chunk c+1 (handle's stream, a few CTAs per SM) runs beside
+    // the issue-bound count sweep of chunk c (aux stream).  The sweep of chunk [a, b) reads slices a-1 .. b,
+    // so classify chunk c covers the slices up to and including cut(c+1).
+    const int z_lo = h->owner_z_min, z_hi = h->zs1;
+    auto cut = [&](int c) { return z_lo + (int)((long long)(z_hi - z_lo) * c / n_chunks); };
+    CU_TRY(h, cudaEventRecord(h->fork_ev, h->stream));
+    CU_TRY(h, cudaStreamWaitEvent(h->aux, h->fork_ev, 0));
+    for (int c = 0; c < n_chunks; ++c) {
+      const int a0 = (c == 0) ? 0 : cut(c) + 1;
+      const int a1 = (c == n_chunks - 1) ? g.Zl : std::min(cut(c + 1) + 1, g.Zl);
+      if (a1 > a0) {
+        DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, a0, a1, h->stream, tuning_knob("CUB_K1_CTAS", 4)));
+        CU_TRY(h, cudaGetLastError());
+      }
+      CU_TRY(h, cudaEventRecord(h->chunk_ev[c], h->stream));
+      CU_TRY(h, cudaStreamWaitEvent(h->aux, h->chunk_ev[c], 0));
+      ca.z_begin = cut(c); ca.z_end = cut(c + 1);
+      CU_TRY(h, dispatch_sweep<MODE_COUNT>(ca, h->aux));
       h->launches++;
     }
+    CU_TRY(h, cudaEventRecord(h->join_ev, h->aux));
+    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->join_ev, 0));
+  }
+  {
+    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
     if (h->timing) cudaEventRecord(h->ev[6], h->stream);
     ScanArgs sa{};
     sa.cnt = h->cnt.p; sa.vofs = h->vofs.p; sa.fofs = h->fofs.p; sa.cofs = h->cofs.p;
@@ -493,8 +530,12 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, mark0, h->d_totals);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
-    t.stop();
-    if (h->timing) cudaEventElapsedTime(&h->ms[7], h->ev[6], h->ev[1]);  // the scan alone
+    if (h->timing) {
+      cudaEventRecord(h->ev[1], h->stream);
+      cudaEventSynchronize(h->ev[1]);
+      cudaEventElapsedTime(&h->ms[1], h->ev[0], h->ev[1]);  // count sweep + scan
+      cudaEventElapsedTime(&h->ms[7], h->ev[6], h->ev[1]);  // the scan alone
+    }
   }
   CU_TRY(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
