@@ -311,9 +311,16 @@ def main():
                              "frac": alg_pipe / (ms_step * 1e-3) / 1e9 / peak,
                              "input_only_frac": own_vox * 4 / (ms_step * 1e-3) / 1e9 / peak}}
 
-    # ---- extras: the full default filter (triangles + projection) ---------------------------------
+    # ---- extras: raster vertex order; the full default filter (triangles + projection) -------------
     extras = {}
     if not args.no_extras:
+        prm1 = capi.default_params()
+        prm1.iso_value, prm1.generate_triangles, prm1.project_vertices = iso, 0, 0
+        prm1.vertex_order = capi.ORDER_RASTER
+        ms1, _, (_, _, tot1) = timed(lambda: step(prm1), max(3, args.steps // 2), 2)
+        extras["raster_vertex_order"] = {"ms_per_step": ms1, "gvoxels_per_s": voxels_total / (ms1 * 1e-3) / 1e9,
+                                         "mfaces_per_s": tot1[1] / (ms1 * 1e-3) / 1e6,
+                                         "note": "CUB_ORDER_RASTER: same mesh up to vertex renumbering (canonical ordering)"}
         prm2 = capi.default_params()
         prm2.iso_value, prm2.generate_triangles, prm2.project_vertices = iso, 1, 1
         prm2.surface_distance_threshold = 0.01 if args.field == "gyroid" else 0.005

@@ -50,6 +50,9 @@ enum {
   CUB_MEM_DEVICE = 1       /* device memory on the handle's device            */
 };
 
+/* ---- vertex numbering ----------------------------------------------------- */
+enum { CUB_ORDER_REFERENCE = 0, CUB_ORDER_RASTER = 1 };
+
 typedef struct cub_handle_s *cub_handle;
 
 /* Filter parameters: the member variables of the reference filter
@@ -61,7 +64,11 @@ typedef struct cub_params {
   int32_t  project_vertices;    /* m_ProjectVerticesToIsoSurface (h:199-201)    */
   int32_t  save_pixel_as_cell_data; /* SavePixelAsCellData (north-star knob; the
                                    reference only has commented stubs txx:314,321,330) */
-  int32_t  reserved0;
+  int32_t  vertex_order;        /* CUB_ORDER_REFERENCE (default): vertex ids in the reference's
+                                   first-touch creation order (txx:179-194);
+                                   CUB_ORDER_RASTER: ids in raster order of the lattice corners -
+                                   same points and connectivity up to that renumbering, about a
+                                   third less work (no ownership sweep, no corner->id map)      */
   double   surface_distance_threshold; /* h:209-210, default 0.5                */
   double   step_length;         /* h:215-216; < 0 means auto = max spacing*0.25
                                    (txx:82-85)                                  */

@@ -136,6 +136,12 @@ public:
   itkSetMacro( SavePixelAsCellData, bool );
   itkBooleanMacro( SavePixelAsCellData );
 
+  /** Extension (default false): number the vertices in raster order of the lattice corners instead of the
+      reference's creation order.  Same points and connectivity up to that renumbering, less GPU work. */
+  itkGetMacro( RasterVertexOrder, bool );
+  itkSetMacro( RasterVertexOrder, bool );
+  itkBooleanMacro( RasterVertexOrder );
+
   /** Projection knobs with the reference's clamp ranges (h:209-228). */
   itkGetMacro( ProjectVertexSurfaceDistanceThreshold, double );
   itkSetClampMacro( ProjectVertexSurfaceDistanceThreshold, double, 0.0, NumericTraits<InputPixelType>::max() );
@@ -159,6 +165,7 @@ protected:
     m_GenerateTriangleFaces = true;
     m_ProjectVerticesToIsoSurface = true;
     m_SavePixelAsCellData = false;
+    m_RasterVertexOrder = false;
     m_ProjectVertexSurfaceDistanceThreshold = 0.5;
     m_ProjectVertexStepLength = -1.0;
     m_ProjectVertexStepLengthRelaxationFactor = 0.95;
@@ -235,6 +242,7 @@ protected:
     params.generate_triangles = m_GenerateTriangleFaces ? 1 : 0;
     params.project_vertices = m_ProjectVerticesToIsoSurface ? 1 : 0;
     params.save_pixel_as_cell_data = m_SavePixelAsCellData ? 1 : 0;
+    params.vertex_order = m_RasterVertexOrder ? CUB_ORDER_RASTER : CUB_ORDER_REFERENCE;
     params.surface_distance_threshold = m_ProjectVertexSurfaceDistanceThreshold;
     params.step_length = m_ProjectVertexStepLength;
     params.step_relaxation = m_ProjectVertexStepLengthRelaxationFactor;
@@ -304,6 +312,7 @@ private:
   bool                m_GenerateTriangleFaces;
   bool                m_ProjectVerticesToIsoSurface;
   bool                m_SavePixelAsCellData;
+  bool                m_RasterVertexOrder;
   double              m_ProjectVertexSurfaceDistanceThreshold;
   double              m_ProjectVertexStepLength;
   double              m_ProjectVertexStepLengthRelaxationFactor;

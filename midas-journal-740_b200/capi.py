@@ -15,6 +15,7 @@ from . import _build
 U8, I8, U16, I16, U32, I32, F32, F64 = range(8)
 MEM_HOST, MEM_DEVICE = 0, 1
 GEN_GYROID, GEN_MARSCHNER_LOBB, GEN_BLOBS = 0, 1, 2
+ORDER_REFERENCE, ORDER_RASTER = 0, 1
 
 DTYPE_CODES = {
     np.dtype(np.uint8): U8, np.dtype(np.int8): I8, np.dtype(np.uint16): U16, np.dtype(np.int16): I16,
@@ -37,7 +38,7 @@ class Params(C.Structure):
         ("generate_triangles", C.c_int32),
         ("project_vertices", C.c_int32),
         ("save_pixel_as_cell_data", C.c_int32),
-        ("reserved0", C.c_int32),
+        ("vertex_order", C.c_int32),
         ("surface_distance_threshold", C.c_double),
         ("step_length", C.c_double),
         ("step_relaxation", C.c_double),

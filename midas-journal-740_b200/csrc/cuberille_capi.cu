@@ -99,7 +99,8 @@ struct cub_handle_s {
   DevBuf<uint2> vtx;
   uint64_t ent_layout[3] = {0, 0, 0};
   int EY = 0, EW = 0;
-  uint64_t n_active = 0;
+  uint64_t n_active = 0, ghost_c = 0;   // active corners of the scanned planes / of the bottom plane (slab below owns them)
+  bool raster = false;
   uint64_t bits_layout[3] = {0, 0, 0};
   DevBuf<unsigned long long> status;  // 2 * n_tiles
   unsigned int* d_ticket = nullptr;
@@ -527,7 +528,9 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * plane_entries : (size_t)-1;
-    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, mark0, h->d_totals);
+    // raster order: the corners of the bottom plane of a slab's range belong to the slab underneath
+    const size_t mark_c = (h->own_z0 > 0) ? (size_t)(h->zs0 + 1) * plane_entries : (size_t)-1;
+    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, h->cofs.p, mark0, mark_c, h->d_totals);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     if (h->timing) {
@@ -549,9 +552,13 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     return fail(h, CUB_ERR_OVERFLOW, "more than 2^32 vertices or faces in one handle (%llu, %llu): split into z-slabs",
                 (unsigned long long)tot_v, (unsigned long long)tot_f);
   h->n_active = h->h_totals[2];
-  h->ghost_v = h->h_totals[3];
   h->ghost_f = h->h_totals[4];
-  h->n_points = tot_v - h->ghost_v;
+  h->ghost_c = h->h_totals[5];
+  h->raster = p->vertex_order == CUB_ORDER_RASTER;
+  // scan-relative vertex ids below ghost_v belong to the slab underneath (first-touch order: what the ghost
+  // slice created; raster order: the corners of the shared bottom plane)
+  h->ghost_v = h->raster ? h->ghost_c : h->h_totals[3];
+  h->n_points = (h->raster ? h->n_active : tot_v) - h->ghost_v;
   h->n_quads = tot_f - h->ghost_f;
   h->point_base = h->cell_base = 0;
   h->counted = true;
@@ -585,8 +592,10 @@ int cub_emit(cub_handle h, int id_bytes) {
   const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
   CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
   CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
-  CUB_TRY(ensure(h, h->vtx, n_pts_all));
-  CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
+  if (!h->raster) {
+    CUB_TRY(ensure(h, h->vtx, n_pts_all));
+    CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
+  }
   if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
   if (cd) CUB_TRY(ensure(h, h->celldata, (size_t)h->n_cells * h->pix_bytes));
 
@@ -595,23 +604,35 @@ int cub_emit(cub_handle h, int id_bytes) {
   const unsigned long long id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
   if (h->n_quads > 0) {
     Timer t(h, 2);
-    {
-      // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
-      SweepArgs a{};
-      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
-      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-      a.vofs = h->vofs.p; a.vtx = h->vtx.p;
-      CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
-      h->launches++;
-    }
-    {
-      // K3b: points + corner -> id map
-      VertexArgs a{};
-      a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
-      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
-      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
-      a.points = h->points.p; a.perm = h->perm.p;
-      k_vertices<<<(unsigned)((n_pts_all + 255) / 256), 256, 0, h->stream>>>(a);
+    if (!h->raster) {
+      {
+        // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
+        SweepArgs a{};
+        a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
+        a.z_begin = h->owner_z_min; a.z_end = h->zs1;
+        a.vofs = h->vofs.p; a.vtx = h->vtx.p;
+        CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
+        h->launches++;
+      }
+      {
+        // K3b: points + corner -> id map
+        VertexArgs a{};
+        a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
+        a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
+        a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
+        a.points = h->points.p; a.perm = h->perm.p;
+        k_vertices<<<(unsigned)((n_pts_all + 255) / 256), 256, 0, h->stream>>>(a);
+        h->launches++;
+        CU_TRY(h, cudaGetLastError());
+      }
+    } else {
+      // raster order: vertex id = corner slot, points straight from the active masks
+      RasterPointArgs a{};
+      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
+      a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
+      a.zg0 = g.zg0; a.geom = h->geom; a.points = h->points.p;
+      const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
+      k_points_raster<<<grid, 256, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     }
@@ -620,7 +641,7 @@ int cub_emit(cub_handle h, int id_bytes) {
       FaceArgs a{};
       a.bits = h->bits.p; a.g = g; a.EY = h->EY; a.EW = h->EW;
       a.z_begin = h->zs0; a.z_end = h->zs1;
-      a.fofs = h->fofs.p; a.act = h->act.p; a.cofs = h->cofs.p; a.perm = h->perm.p;
+      a.fofs = h->fofs.p; a.act = h->act.p; a.cofs = h->cofs.p; a.perm = h->raster ? nullptr : h->perm.p;
       a.ghost_f = (uint32_t)h->ghost_f;
       a.id_delta = id_delta;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;

@@ -171,12 +171,15 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
   }
 }
 
-// reads the exclusive offsets at the first own entry (slab runs: what the ghost slice below contributed)
-__global__ void k_gather_marks(const uint32_t* __restrict__ vofs, const uint32_t* __restrict__ fofs, size_t mark0,
-                               unsigned long long* out /* [3..4] */) {
+// reads the exclusive offsets at the first own entry (slab runs: what the ghost slice below contributed) and
+// the number of active corners of the bottom plane of the own range (owned by the slab underneath)
+__global__ void k_gather_marks(const uint32_t* __restrict__ vofs, const uint32_t* __restrict__ fofs,
+                               const uint32_t* __restrict__ cofs, size_t mark0, size_t mark_c,
+                               unsigned long long* out /* [3..5] */) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     out[3] = (mark0 != (size_t)-1) ? vofs[mark0] : 0ull;
     out[4] = (mark0 != (size_t)-1) ? fofs[mark0] : 0ull;
+    out[5] = (mark_c != (size_t)-1) ? cofs[mark_c] : 0ull;
   }
 }
 

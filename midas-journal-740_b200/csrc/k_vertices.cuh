@@ -46,4 +46,36 @@ __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
   }
 }
 
+// Raster vertex order (CUB_ORDER_RASTER): vertex id = slot, so the points follow directly from the active
+// masks: one thread per corner word, ids cofs[word] + rank are consecutive inside a word.
+struct RasterPointArgs {
+  const uint32_t* act;
+  const uint32_t* cofs;
+  int EY, EW, Wc;
+  int plane_lo, plane_hi;   // local corner planes to emit (inclusive)
+  int zg0;
+  Geom geom;
+  float* points;            // indexed by slot
+};
+
+__global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) {
+  // grid: x = 32-word segments of a corner row, y = groups of 8 rows (one per warp), z = planes
+  const int w = blockIdx.x * 32 + (threadIdx.x & 31), cy = blockIdx.y * 8 + (threadIdx.x >> 5), cz = a.plane_lo + blockIdx.z;
+  if (w >= a.Wc || cy >= a.EY) return;
+  const size_t e = ((size_t)cz * a.EY + cy) * a.EW + w;
+  uint32_t m = __ldg(a.act + e);
+  if (!m) return;
+  uint32_t id = __ldg(a.cofs + e);
+  const float py = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy);
+  const float pz = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz + a.zg0);
+  while (m) {
+    const int b = __ffs(m) - 1;
+    m &= m - 1;
+    float* p = a.points + 3 * (size_t)id++;
+    p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], 32 * w + b);
+    p[1] = py;
+    p[2] = pz;
+  }
+}
+
 }  // namespace cub

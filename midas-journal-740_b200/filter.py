@@ -46,6 +46,7 @@ class CuberilleImageToMeshFilter:
         self._triangles = True
         self._project = True
         self._cell_data = False
+        self._raster_order = False
         self._thr = 0.5
         self._step = -1.0
         self._relax = 0.95
@@ -79,6 +80,9 @@ class CuberilleImageToMeshFilter:
     def GetSavePixelAsCellData(self): return self._cell_data
     def SavePixelAsCellDataOn(self): self.SetSavePixelAsCellData(True)
     def SavePixelAsCellDataOff(self): self.SetSavePixelAsCellData(False)
+    # extension: number the vertices in lattice-corner raster order instead of the reference's creation order
+    def SetRasterVertexOrder(self, b): self._set("_raster_order", bool(b))
+    def GetRasterVertexOrder(self): return self._raster_order
 
     def SetProjectVertexSurfaceDistanceThreshold(self, v):
         # itkSetClampMacro(.., 0.0, NumericTraits<InputPixelType>::max())  h:210
@@ -103,6 +107,7 @@ class CuberilleImageToMeshFilter:
         p.generate_triangles = int(self._triangles)
         p.project_vertices = int(self._project)
         p.save_pixel_as_cell_data = int(self._cell_data)
+        p.vertex_order = capi.ORDER_RASTER if self._raster_order else capi.ORDER_REFERENCE
         p.surface_distance_threshold = self._thr
         p.step_length = self._step
         p.step_relaxation = self._relax

@@ -4,7 +4,7 @@ the kernel reproduces the oracle's arithmetic, which is tighter than the 1e-5 x 
 import numpy as np
 import pytest
 
-from util import KAT, KAT_ARGS, assert_mesh_equal, gyroid, oracle, pkg, random_volume, read_fixture, run_filter, smooth_volume
+from util import KAT, KAT_ARGS, assert_mesh_equal, assert_mesh_equal_up_to_vertex_order, gyroid, oracle, pkg, random_volume, read_fixture, run_filter, smooth_volume
 
 pytestmark = pytest.mark.gpu
 
@@ -227,3 +227,61 @@ def test_filter_rerun_with_changed_parameters_and_inputs():
         f.Update()
         ref = O.cuberille(img.data, iso, triangles=tri, project=True, step=0.24)
         assert_mesh_equal(f.GetOutput(), ref, fixture)
+
+
+@pytest.mark.parametrize("fixture,iso,tri,proj", [("fuel", 15, True, True), ("neghip", 55, False, False), ("nucleon", 140, True, False),
+                                                  ("silicium", 85, False, True), ("blob3", 200, True, True)])
+def test_raster_vertex_order_is_a_renumbering_of_the_reference_mesh(fixture, iso, tri, proj):
+    """CUB_ORDER_RASTER: bit-exact connectivity, vertex count and positions after canonical ordering"""
+    O = oracle()
+    img = read_fixture(fixture)
+    args = dict(max_steps=100, **KAT_ARGS)
+    ref = O.cuberille(img.data, iso, triangles=tri, project=proj, **args)
+    ref0 = O.cuberille(img.data, iso, triangles=tri, project=False)
+    mesh = run_filter(img, iso, triangles=tri, project=proj, raster_order=True, **args)
+    mesh0 = run_filter(img, iso, triangles=tri, project=False, raster_order=True)
+    assert_mesh_equal_up_to_vertex_order(mesh, ref, mesh0, ref0, fixture)
+
+
+@pytest.mark.parametrize("dtype,shape", [(np.uint8, (9, 33, 65)), (np.float32, (6, 7, 8)), (np.int16, (12, 40, 200)), (np.uint8, (1, 1, 1))])
+def test_raster_vertex_order_on_noise(dtype, shape):
+    O = oracle()
+    vol, iso = random_volume(shape, dtype, seed=17)
+    ref = O.cuberille(vol, iso, triangles=False, project=False, mode=O.CLOSED_FORM, cell_data=True)
+    mesh = run_filter(vol, iso, triangles=False, project=False, raster_order=True, cell_data=True)
+    assert_mesh_equal_up_to_vertex_order(mesh, ref, mesh, ref, "noise")
+
+
+@pytest.mark.parametrize("tri,proj", [(False, False), (True, True)])
+def test_raster_vertex_order_z_slabs(tri, proj):
+    """slabs in raster order: the corners of a shared plane belong to the lower slab"""
+    P, O = pkg(), oracle()
+    vol = gyroid((41, 30, 50), 13.0)
+    nz, n_slabs = vol.shape[0], 3
+    bounds = np.linspace(0, nz, n_slabs + 1).astype(int)
+
+    def run(project):
+        p = P.capi.default_params()
+        p.iso_value, p.generate_triangles, p.project_vertices, p.surface_distance_threshold = 0.0, int(tri), int(project), 0.01
+        p.vertex_order = P.capi.ORDER_RASTER
+        hs, counts = [], []
+        for s in range(n_slabs):
+            z0, z1 = int(bounds[s]), int(bounds[s + 1])
+            lo, hi = max(0, z0 - 9), min(nz, z1 + 9)
+            h = P.capi.Handle(0)
+            h.set_volume(vol[lo:hi])
+            h.set_slab(nz, lo, z0, z1)
+            counts.append(h.count(p))
+            hs.append(h)
+        pts, cells, pbase = [], [], 0
+        for h, (np_, nq) in zip(hs, counts):
+            h.set_id_base(pbase, 0)
+            h.emit(4)
+            a, b, _ = h.fetch()
+            pts.append(a); cells.append(b); pbase += np_
+            h.close()
+        return P.Mesh(np.concatenate(pts), np.concatenate(cells))
+
+    ref = O.cuberille(vol, 0.0, triangles=tri, project=proj, thr=0.01)
+    ref0 = O.cuberille(vol, 0.0, triangles=tri, project=False)
+    assert_mesh_equal_up_to_vertex_order(run(proj), ref, run(False), ref0, "raster slabs")

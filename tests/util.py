@@ -102,7 +102,7 @@ def smooth_volume(shape, dtype, seed, scale=60.0):
 
 
 def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5, step=-1.0, relax=0.95, max_steps=50,
-               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), raster_order=False):
     """Drive the CUDA path through the filter mirror, with the reference driver's call sequence
     (Testing/CuberilleTest01.cxx:144-162)."""
     P = pkg()
@@ -113,6 +113,7 @@ def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5,
     f.SetGenerateTriangleFaces(triangles)
     f.SetProjectVerticesToIsoSurface(project)
     f.SetSavePixelAsCellData(cell_data)
+    f.SetRasterVertexOrder(raster_order)
     f.SetProjectVertexSurfaceDistanceThreshold(thr)
     if step >= 0:
         f.SetProjectVertexStepLength(step)
@@ -133,3 +134,22 @@ def assert_mesh_equal(mesh, ref, what=""):
         raise AssertionError(f"{what}: {bad.size} points differ, first {bad[0]}: {mesh.points[bad[0]]} vs {ref.points[bad[0]]}")
     if ref.cell_data is not None:
         assert mesh.cell_data is not None and np.array_equal(mesh.cell_data, ref.cell_data), f"{what}: cell data differs"
+
+
+def assert_mesh_equal_up_to_vertex_order(mesh, ref, mesh_unprojected, ref_unprojected, what=""):
+    """raster vertex order: same points, cells and cell order as the reference after renumbering the vertices.
+    The renumbering is recovered from the UNPROJECTED meshes (lattice positions are unique and exact) and then
+    applied to the meshes under test (vertex numbering does not depend on the projection)."""
+    assert mesh.points.shape == ref.points.shape, f"{what}: #points {mesh.points.shape} vs {ref.points.shape}"
+    assert mesh.cells.shape == ref.cells.shape, f"{what}: #cells"
+    key = {p.tobytes(): i for i, p in enumerate(ref_unprojected.points)}
+    assert len(key) == ref_unprojected.points.shape[0]
+    to_ref = np.array([key[p.tobytes()] for p in mesh_unprojected.points], np.int64)
+    assert np.array_equal(np.sort(to_ref), np.arange(to_ref.size)), f"{what}: not a renumbering"
+    # raster order = sorted by (z, y, x) of the lattice corner
+    o = np.lexsort((mesh_unprojected.points[:, 0], mesh_unprojected.points[:, 1], mesh_unprojected.points[:, 2]))
+    assert np.array_equal(o, np.arange(o.size)), f"{what}: vertices are not in corner raster order"
+    assert np.array_equal(mesh.points.view(np.uint32), ref.points[to_ref].view(np.uint32)), f"{what}: positions differ"
+    assert np.array_equal(to_ref[mesh.cells.astype(np.int64)], ref.cells.astype(np.int64)), f"{what}: connectivity differs"
+    if ref.cell_data is not None:
+        assert np.array_equal(mesh.cell_data, ref.cell_data)
