@@ -14,6 +14,8 @@
 // clamped (the reference reads out of bounds) and a zero gradient stops the vertex where it is
 // (the reference divides by zero).
 #pragma once
+#include <climits>
+
 #include "cub_common.cuh"
 
 namespace cub {
@@ -29,6 +31,7 @@ struct ProjArgs {
   unsigned max_steps;
   float* points;
   size_t n_points;
+  unsigned long long* work;  // device counter (zeroed before the launch): next vertex to hand out
 };
 
 template <typename T>
@@ -79,10 +82,11 @@ __device__ __forceinline__ void gradient_at(const VolView<T>& v, const float c[3
 
 __device__ __forceinline__ int clampi(long long v, int hi) { return v < 0 ? 0 : (v > hi ? hi : (int)v); }
 
+// Persistent lanes: the number of moves varies from 0 to max_steps+2 between vertices, so a lane that finishes
+// its vertex immediately takes the next one from a global counter instead of idling until the slowest vertex of
+// its warp is done.  The arithmetic per vertex is unchanged (and so are the results, bit for bit).
 template <typename T>
 __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= a.n_points) return;
   VolView<T> v{static_cast<const T*>(a.vol), a.g.X, a.g.Y, a.g.Zl, a.g.zg0, a.g.Zg};
   float gc[3];
   double inv_sp[3];
@@ -91,12 +95,29 @@ __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
     inv_sp[k] = 1.0 / a.geom.spacing[k];
     gc[k] = (float)(0.5 * inv_sp[k]);
   }
-  float vert[3] = {a.points[3 * i], a.points[3 * i + 1], a.points[3 * i + 2]};
-
-  bool done = false;
+  size_t i = 0;
+  bool have = false;
+  float vert[3] = {0.f, 0.f, 0.f};
   double step = a.step0;
   unsigned numberOfSteps = 0;
-  while (!done) {
+
+  // The 8 lattice nodes around the vertex: their pixel values and fp32 central-difference gradients are kept
+  // in registers and only re-fetched when the vertex crosses into another cell (a step is a fraction of a
+  // voxel, so most iterations stay in the cell: the first version re-read 64 voxels per iteration).
+  long long cell[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
+  double nval[8];
+  float ngrad[8][3];
+
+  while (true) {
+    if (!have) {
+      i = (size_t)atomicAdd(a.work, 1ull);
+      if (i >= a.n_points) break;
+      vert[0] = a.points[3 * i]; vert[1] = a.points[3 * i + 1]; vert[2] = a.points[3 * i + 2];
+      step = a.step0;
+      numberOfSteps = 0;
+      have = true;
+    }
+    bool done = false;  // one pass of the reference's `while ( !done )` body (txx:448-473)
     // continuous index, base index and distances (shared by both interpolators)
     long long base[3];
     double dist[3];
@@ -106,6 +127,17 @@ __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
       const double f = floor(ci);
       base[k] = (long long)f;
       dist[k] = ci - f;
+    }
+    if (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2]) {
+      cell[0] = base[0]; cell[1] = base[1]; cell[2] = base[2];
+#pragma unroll
+      for (int counter = 0; counter < 8; ++counter) {
+        const int cx = clampi(base[0] + ((counter & 1) ? 1 : 0), v.X - 1);
+        const int cy = clampi(base[1] + ((counter & 2) ? 1 : 0), v.Y - 1);
+        const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
+        gradient_at(v, gc, cx, cy, cz, ngrad[counter]);
+        nval[counter] = (double)v.at(cx, cy, cz);
+      }
     }
     double gd[3] = {0.0, 0.0, 0.0};
     double value = 0.0, total = 0.0;
@@ -118,16 +150,10 @@ __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
         overlap *= (counter & 2) ? dist[1] : 1.0 - dist[1];
         overlap *= (counter & 4) ? dist[2] : 1.0 - dist[2];
         if (overlap != 0.0) {
-          const long long nx = base[0] + ((counter & 1) ? 1 : 0);
-          const long long ny = base[1] + ((counter & 2) ? 1 : 0);
-          const long long nz = base[2] + ((counter & 4) ? 1 : 0);
-          const int cx = clampi(nx, v.X - 1), cy = clampi(ny, v.Y - 1), cz = clampi(nz, v.Zg - 1);
-          float g[3];
-          gradient_at(v, gc, cx, cy, cz, g);
-          gd[0] += overlap * (double)g[0];
-          gd[1] += overlap * (double)g[1];
-          gd[2] += overlap * (double)g[2];
-          value += overlap * (double)v.at(cx, cy, cz);
+          gd[0] += overlap * (double)ngrad[counter][0];
+          gd[1] += overlap * (double)ngrad[counter][1];
+          gd[2] += overlap * (double)ngrad[counter][2];
+          value += overlap * nval[counter];
           total += overlap;
         }
         if (total == 1.0) open = false;
@@ -142,21 +168,27 @@ __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
       sq += c * c;
     }
     const double norm = sqrt(sq);
-    if (norm == 0.0) break;
+    if (norm == 0.0) {
+      done = true;  // zero gradient: the vertex stays where it is
+    } else {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
-
-    done |= fabs(value - a.iso) < a.thr;  // txx:456
-    if (done) break;
-    const double sign = (value < a.iso) ? +1.0 : -1.0;  // txx:463
+      for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+      done |= fabs(value - a.iso) < a.thr;  // txx:456
+      if (!done) {
+        const double sign = (value < a.iso) ? +1.0 : -1.0;  // txx:463
 #pragma unroll
-    for (int k = 0; k < 3; ++k) vert[k] = (float)((double)vert[k] + ((double)normal[k] * sign) * step);  // txx:466
-    step *= a.relax;                                  // txx:468
-    done |= numberOfSteps++ > a.max_steps;            // txx:469
+        for (int k = 0; k < 3; ++k) vert[k] = (float)((double)vert[k] + ((double)normal[k] * sign) * step);  // txx:466
+        step *= a.relax;                                  // txx:468
+        done |= numberOfSteps++ > a.max_steps;            // txx:469
+      }
+    }
+    if (done) {
+      a.points[3 * i] = vert[0];
+      a.points[3 * i + 1] = vert[1];
+      a.points[3 * i + 2] = vert[2];
+      have = false;
+    }
   }
-  a.points[3 * i] = vert[0];
-  a.points[3 * i + 1] = vert[1];
-  a.points[3 * i + 2] = vert[2];
 }
 
 }  // namespace cub
