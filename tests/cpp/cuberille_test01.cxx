@@ -1,5 +1,5 @@
-// CuberilleTest01.cxx — the reference's test driver (Testing/CuberilleTest01.cxx:57-213), rebuilt
-// around include/itkCuberilleImageToMeshFilter.h.  Same command line:
+// cuberille_test01.cxx — a test driver with the command line and behaviour of the reference's
+// Testing/CuberilleTest01.cxx (57-213), written around include/itkCuberilleImageToMeshFilter.h.  Command line:
 //   CuberilleTest01 InputImage OutputMesh IsoSurfaceValue ExpectedNumberOfPoints ExpectedNumberOfCells
 //                   [GenerateTriangleFaces] [ProjectToIsoSurface] [SurfaceDistanceThreshold] [StepLength]
 //                   [StepLengthRelax] [MaximumNumberOfSteps]
@@ -99,84 +99,95 @@ static void WriteVTKPolyData( const char * filename, MeshType * mesh )
     }
 }
 
+// Command line of the reference driver (Testing/CuberilleTest01.cxx:83-109): five required positionals, then up
+// to six optional ones with the reference's defaults.
+struct Options
+{
+  std::string input, output;
+  int iso = 0;
+  unsigned long expectedPoints = 0, expectedCells = 0;
+  bool triangles = true, project = true;
+  double threshold = 0.5, stepLength = 0.25, relax = 0.95;
+  unsigned int maxSteps = 50;
+
+  static bool Parse( int argc, char ** argv, Options & o )
+  {
+    if ( argc < 6 ) return false;
+    std::vector<std::string> a( argv + 1, argv + argc );
+    o.input = a[0];
+    o.output = a[1];
+    o.iso = std::atoi( a[2].c_str() );
+    o.expectedPoints = std::strtoul( a[3].c_str(), 0, 10 );
+    o.expectedCells = std::strtoul( a[4].c_str(), 0, 10 );
+    if ( a.size() > 5 ) o.triangles = std::atoi( a[5].c_str() ) != 0;
+    if ( a.size() > 6 ) o.project = std::atoi( a[6].c_str() ) != 0;
+    if ( a.size() > 7 ) o.threshold = std::atof( a[7].c_str() );
+    if ( a.size() > 8 ) o.stepLength = std::atof( a[8].c_str() );
+    if ( a.size() > 9 ) o.relax = std::atof( a[9].c_str() );
+    if ( a.size() > 10 ) o.maxSteps = (unsigned int)std::atoi( a[10].c_str() );
+    return true;
+  }
+};
+
 int Test01( int argc, char * argv [] )
 {
-try
-  {
-  if ( argc < 6 )
+  Options opt;
+  if ( !Options::Parse( argc, argv, opt ) )
     {
-    std::cout << "USAGE: " << argv[0];
-    std::cout << " InputImage OutputMesh IsoSurfaceValue ExpectedNumberOfPoints ExpectedNumberOfCells";
-    std::cout << " [GenerateTriangleFaces] [ProjectToIsoSurface]";
-    std::cout << " [SurfaceDistanceThreshold] [StepLength] [StepLengthRelax] [MaximumNumberOfSteps]" << std::endl;
+    std::cout << "USAGE: " << argv[0]
+              << " InputImage OutputMesh IsoSurfaceValue ExpectedNumberOfPoints ExpectedNumberOfCells"
+              << " [GenerateTriangleFaces] [ProjectToIsoSurface]"
+              << " [SurfaceDistanceThreshold] [StepLength] [StepLengthRelax] [MaximumNumberOfSteps]" << std::endl;
     return EXIT_FAILURE;
     }
-  int arg = 1;
-  char * FilenameInputImage = argv[arg++];
-  char * FilenameOutputMesh = argv[arg++];
-  PixelType IsoSurfaceValue = atoi( argv[arg++] );
-  unsigned int ExpectedNumberOfPoints = atoi( argv[arg++] );
-  unsigned int ExpectedNumberOfCells = atoi( argv[arg++] );
-  bool GenerateTriangleFaces = true;
-  if ( argc > arg ) GenerateTriangleFaces = atoi( argv[arg++] );
-  bool ProjectToIsoSurface = true;
-  if ( argc > arg ) ProjectToIsoSurface = atoi( argv[arg++] );
-  double SurfaceDistanceThreshold = 0.5;
-  if ( argc > arg ) SurfaceDistanceThreshold = atof( argv[arg++] );
-  double StepLength = 0.25;
-  if ( argc > arg ) StepLength = atof( argv[arg++] );
-  double StepLengthRelax = 0.95;
-  if ( argc > arg ) StepLengthRelax = atof( argv[arg++] );
-  unsigned int MaximumNumberOfSteps = 50;
-  if ( argc > arg ) MaximumNumberOfSteps = atoi( argv[arg++] );
-
-  std::cout << "Reading input image: " << FilenameInputImage << std::endl;
-  ImageType::Pointer input = ReadMetaImage( FilenameInputImage );
-
-  std::cout << "Creating cuberille mesh..." << std::endl;
-  CuberilleType::Pointer cuberille = CuberilleType::New();
-  cuberille->SetInput( input );
-  cuberille->SetIsoSurfaceValue( IsoSurfaceValue );
-  InterpolatorType::Pointer interpolator = InterpolatorType::New();
-  cuberille->SetInterpolator( interpolator );
-  cuberille->SetGenerateTriangleFaces( GenerateTriangleFaces );
-  cuberille->SetProjectVerticesToIsoSurface( ProjectToIsoSurface );
-  cuberille->SetProjectVertexSurfaceDistanceThreshold( SurfaceDistanceThreshold );
-  cuberille->SetProjectVertexStepLength( StepLength );
-  cuberille->SetProjectVertexStepLengthRelaxationFactor( StepLengthRelax );
-  cuberille->SetProjectVertexMaximumNumberOfSteps( MaximumNumberOfSteps );
-  const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  cuberille->Update();
-  const double seconds = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
-  MeshType::Pointer outputMesh = cuberille->GetOutput();
-  outputMesh->DisconnectPipeline();
-
-  std::cout << "Writing output mesh: " << FilenameOutputMesh << std::endl;
-  WriteVTKPolyData( FilenameOutputMesh, outputMesh );
-
-  std::cout << "Polygonization took " << seconds << " seconds" << std::endl;
-  std::cout << "Mesh has " << outputMesh->GetNumberOfPoints() << " vertices ";
-  std::cout << "and " << outputMesh->GetNumberOfCells() << " cells" << std::endl;
-  if ( ExpectedNumberOfPoints > 0 && outputMesh->GetNumberOfPoints() != ExpectedNumberOfPoints )
+  try
     {
-    std::cerr << "ERROR: Expected mesh with " << ExpectedNumberOfPoints
-              << " points, but found " << outputMesh->GetNumberOfPoints() << std::endl;
+    std::cout << "Reading input image: " << opt.input << std::endl;
+    ImageType::Pointer input = ReadMetaImage( opt.input.c_str() );
+
+    // the filter is configured through the same setters, in the same order, as Test:144-157
+    std::cout << "Creating cuberille mesh..." << std::endl;
+    CuberilleType::Pointer filter = CuberilleType::New();
+    filter->SetInput( input );
+    filter->SetIsoSurfaceValue( static_cast<PixelType>( opt.iso ) );
+    filter->SetInterpolator( InterpolatorType::New() );
+    filter->SetGenerateTriangleFaces( opt.triangles );
+    filter->SetProjectVerticesToIsoSurface( opt.project );
+    filter->SetProjectVertexSurfaceDistanceThreshold( opt.threshold );
+    filter->SetProjectVertexStepLength( opt.stepLength );
+    filter->SetProjectVertexStepLengthRelaxationFactor( opt.relax );
+    filter->SetProjectVertexMaximumNumberOfSteps( opt.maxSteps );
+
+    const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    filter->Update();
+    const double seconds = std::chrono::duration<double>( std::chrono::steady_clock::now() - t0 ).count();
+    MeshType::Pointer mesh = filter->GetOutput();
+    mesh->DisconnectPipeline();
+
+    std::cout << "Writing output mesh: " << opt.output << std::endl;
+    WriteVTKPolyData( opt.output.c_str(), mesh );
+
+    // same report and pass/fail rule as Test:190-204 (an expected count of 0 means "do not check")
+    std::cout << "Polygonization took " << seconds << " seconds" << std::endl;
+    std::cout << "Mesh has " << mesh->GetNumberOfPoints() << " vertices and " << mesh->GetNumberOfCells() << " cells" << std::endl;
+    int status = EXIT_SUCCESS;
+    if ( opt.expectedPoints > 0 && mesh->GetNumberOfPoints() != opt.expectedPoints )
+      {
+      std::cerr << "ERROR: Expected mesh with " << opt.expectedPoints << " points, but found " << mesh->GetNumberOfPoints() << std::endl;
+      status = EXIT_FAILURE;
+      }
+    if ( opt.expectedCells > 0 && mesh->GetNumberOfCells() != opt.expectedCells )
+      {
+      std::cerr << "ERROR: Expected mesh with " << opt.expectedCells << " cells, but found " << mesh->GetNumberOfCells() << std::endl;
+      status = EXIT_FAILURE;
+      }
+    return status;
+    }
+  catch ( itk::ExceptionObject & err )
+    {
+    std::cerr << "ExceptionObject caught !" << std::endl << err << std::endl;
     return EXIT_FAILURE;
     }
-  if ( ExpectedNumberOfCells > 0 && outputMesh->GetNumberOfCells() != ExpectedNumberOfCells )
-    {
-    std::cerr << "ERROR: Expected mesh with " << ExpectedNumberOfCells
-              << " cells, but found " << outputMesh->GetNumberOfCells() << std::endl;
-    return EXIT_FAILURE;
-    }
-  return EXIT_SUCCESS;
-  }
-catch ( itk::ExceptionObject & err )
-  {
-  std::cerr << "ExceptionObject caught !" << std::endl;
-  std::cerr << err << std::endl;
-  return EXIT_FAILURE;
-  }
 }
 
 int main( int argc, char * argv [] )

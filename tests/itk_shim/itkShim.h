@@ -1,7 +1,7 @@
 // itkShim.h — a MINIMAL stand-in for the ITK classes the cuberille adapter touches
 // (SURVEY.md §8b "ITK surface the adapter needs").  ITK itself is not installable in this
 // environment (no network, no vendored copy); this shim exists only so that
-// include/itkCuberilleImageToMeshFilter.h and tests/cpp/CuberilleTest01.cxx can be compiled
+// include/itkCuberilleImageToMeshFilter.h and tests/cpp/cuberille_test01.cxx can be compiled
 // and run here with the same source text a real ITK build would see.  It is test
 // infrastructure: nothing in the product includes it.
 #ifndef itkShim_h

@@ -1,5 +1,5 @@
 """The C++ drop-in: include/itkCuberilleImageToMeshFilter.h compiled against the minimal ITK stand-in and
-driven by tests/cpp/CuberilleTest01.cxx with the reference's own command lines (Testing/CMakeLists.txt)."""
+driven by tests/cpp/cuberille_test01.cxx with the reference's own command lines (Testing/CMakeLists.txt)."""
 import os
 import subprocess
 
