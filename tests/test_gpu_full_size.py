@@ -1,0 +1,108 @@
+"""GPU: BASELINE.json-size workloads checked through size-independent properties (the oracle would need
+minutes here): generated on the device, run through the C-ABI, mesh pulled back and checked with numpy.
+
+* every vertex id is used, every quad is a unit square (unprojected positions are exact lattice corners)
+* the surface is closed: the generators force the outermost voxel layer outside, so every undirected edge is
+  shared by an even number of quads (2, or 4 where two sheets touch along an edge)
+* Euler-Poincare style count: for a quad mesh in which every edge has multiplicity m_e, sum m_e = 4 F
+* idempotence: a second run on the same handle gives the same bytes
+* z-slab decomposition (4 slabs) concatenates to the same bytes
+* raster vertex order is a renumbering: same sorted point set, same cells after relabelling
+* a z-sub-slab of the same bytes goes through the oracle (bit-exact), so the properties are anchored
+"""
+import numpy as np
+import pytest
+
+from util import assert_mesh_equal, oracle, pkg
+
+pytestmark = pytest.mark.gpu
+
+
+def _run(P, h, tri=False, proj=False, order=0, thr=0.5):
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices, p.vertex_order = h._iso, int(tri), int(proj), order
+    p.surface_distance_threshold = thr
+    h.run(p)
+    pts, cells, _ = h.fetch()
+    return pts, cells
+
+
+@pytest.mark.parametrize("kind,size,p0,iso", [("gyroid", 512, 64.0, 0.0), ("marschner_lobb", 512, 0.0, 0.5), ("blobs", 384, 48.0, 0.5)])
+def test_full_size_properties(kind, size, p0, iso):
+    P = pkg()
+    gen = {"gyroid": P.capi.GEN_GYROID, "marschner_lobb": P.capi.GEN_MARSCHNER_LOBB, "blobs": P.capi.GEN_BLOBS}[kind]
+    h = P.capi.Handle(0)
+    h.generate(gen, (size, size, size), p0=p0, p1=1.0)
+    h._iso = iso
+    pts, quads = _run(P, h)
+    n, f = pts.shape[0], quads.shape[0]
+    assert f > 100000 and n > 100000
+    # ids: dense, all used
+    assert int(quads.max()) == n - 1
+    used = np.zeros(n, bool)
+    used[quads.reshape(-1)] = True
+    assert used.all()
+    # exact lattice positions, unit squares
+    assert np.array_equal(pts + 0.5, np.rint(pts + 0.5))
+    q = pts[quads.astype(np.int64)]
+    edge = np.abs(q - np.roll(q, -1, axis=1)).sum(axis=2)
+    assert np.all(edge == 1.0)
+    # closed surface: even edge multiplicities, sum = 4F
+    a = quads.astype(np.uint64)
+    b = np.roll(a, -1, axis=1)
+    lo, hi = np.minimum(a, b), np.maximum(a, b)
+    keys = (lo << np.uint64(32) | hi).reshape(-1)
+    _, mult = np.unique(keys, return_counts=True)
+    assert mult.sum() == 4 * f
+    assert np.all(mult % 2 == 0) and mult.max() <= 4
+    # no empty interior slice (the reference's lookup-plane quirk is not in play)
+    vol = h.download_volume()
+    inside = (vol >= iso)
+    occ = inside.reshape(size, -1).any(axis=1)
+    assert occ[1:-1].all() or kind == "marschner_lobb"
+    # idempotence
+    pts2, quads2 = _run(P, h)
+    assert np.array_equal(pts.view(np.uint32), pts2.view(np.uint32)) and np.array_equal(quads, quads2)
+    # raster vertex order: a renumbering
+    rp, rq = _run(P, h, order=P.capi.ORDER_RASTER)
+    assert rp.shape == pts.shape and rq.shape == quads.shape
+    key = {}
+    view = np.ascontiguousarray(pts).view([("x", "f4"), ("y", "f4"), ("z", "f4")]).reshape(-1)
+    order_ref = np.argsort(view, order=("z", "y", "x"))
+    assert np.array_equal(np.ascontiguousarray(rp).view(view.dtype).reshape(-1), view[order_ref])  # raster order = sorted corners
+    to_ref = order_ref  # raster id k is reference id order_ref[k]
+    assert np.array_equal(to_ref[rq.astype(np.int64)], quads.astype(np.int64))
+    # z-slabs: 4 slabs, 2-slice halo, concatenation equals the single run
+    bounds = np.linspace(0, size, 5).astype(int)
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = iso, 0, 0
+    hs, counts = [], []
+    for s in range(4):
+        z0, z1 = int(bounds[s]), int(bounds[s + 1])
+        lo_, hi_ = max(0, z0 - 2), min(size, z1 + 2)
+        hh = P.capi.Handle(0)
+        hh.generate(gen, (size, size, hi_ - lo_), (size, size, size), lo_, p0, 1.0)
+        hh.set_slab(size, lo_, z0, z1)
+        counts.append(hh.count(p))
+        hs.append(hh)
+    pbase, parts_p, parts_c = 0, [], []
+    for hh, (np_, nq) in zip(hs, counts):
+        hh.set_id_base(pbase, 0)
+        hh.emit(4)
+        a_, b_, _ = hh.fetch()
+        parts_p.append(a_); parts_c.append(b_); pbase += np_
+        hh.close()
+    assert np.array_equal(np.concatenate(parts_p).view(np.uint32), pts.view(np.uint32))
+    assert np.array_equal(np.concatenate(parts_c), quads)
+    # anchor: a 24-slice sub-slab of the same bytes through the oracle
+    O = oracle()
+    z0 = size // 2
+    sub = np.ascontiguousarray(vol[z0:z0 + 24])
+    ref = O.cuberille(sub, iso, triangles=True, project=True, thr=0.01 if kind == "gyroid" else 0.005)
+    hs2 = P.capi.Handle(0)
+    hs2.set_volume(sub)
+    hs2._iso = iso
+    sp, sc = _run(P, hs2, tri=True, proj=True, thr=0.01 if kind == "gyroid" else 0.005)
+    assert_mesh_equal(P.Mesh(sp, sc), ref, f"{kind} sub-slab")
+    hs2.close()
+    h.close()
