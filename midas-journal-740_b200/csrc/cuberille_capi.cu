@@ -473,7 +473,13 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   // K2 scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
   const size_t e_begin = (size_t)h->owner_z_min * plane_entries;
   const size_t n_scan = (size_t)(h->zs1 + 1 - h->owner_z_min) * plane_entries;
-  const size_t n_tiles = (n_scan + kScanTile - 1) / kScanTile;
+  // one large scan tile per resident CTA (4 CTAs/SM), so that every tile is in flight when the look-backs run
+  int scan_occ = 0;
+  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_count_scan, kScanThreads, 0));
+  const size_t max_tiles = (size_t)kNumSMs * std::max(1, std::min(scan_occ, tuning_knob("CUB_SCAN_CTAS_PER_SM", 8)));
+  size_t scan_tile = ((n_scan + max_tiles - 1) / max_tiles + kScanTile - 1) / kScanTile * kScanTile;
+  if (scan_tile < (size_t)kScanTile) scan_tile = kScanTile;
+  const size_t n_tiles = (n_scan + scan_tile - 1) / scan_tile;
   CUB_TRY(ensure(h, h->status, 3 * n_tiles));
   SweepArgs ca{};
   ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
@@ -525,9 +531,8 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     sa.cnt = h->cnt.p; sa.vofs = h->vofs.p; sa.fofs = h->fofs.p; sa.cofs = h->cofs.p;
     sa.e_begin = e_begin; sa.n = n_scan;
     sa.plane_entries = (unsigned)plane_entries; sa.plane_lo = (unsigned)h->zs0;
-    sa.status = h->status.p; sa.n_tiles = (unsigned)n_tiles; sa.ticket = h->d_ticket; sa.totals = h->d_totals;
-    const unsigned scan_ctas = (unsigned)std::min<size_t>(n_tiles, (size_t)kNumSMs * tuning_knob("CUB_SCAN_CTAS_PER_SM", 4));
-    k_count_scan<<<scan_ctas, kScanThreads, 0, h->stream>>>(sa);
+    sa.status = h->status.p; sa.n_tiles = (unsigned)n_tiles; sa.tile = scan_tile; sa.ticket = h->d_ticket; sa.totals = h->d_totals;
+    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * plane_entries : (size_t)-1;

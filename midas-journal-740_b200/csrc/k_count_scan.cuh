@@ -9,8 +9,8 @@
 // K2a (k_sweep.cuh, MODE_COUNT) leaves one packed count per entry of the [Zl+1][EY][EW] lattice
 // (owned corners | faces << 10 | active corners << 20).  This kernel turns them into the three
 // exclusive-offset arrays vofs / fofs / cofs: each thread takes 16 consecutive entries (four 16-byte
-// loads), a block-wide scan combines the 4096 entries of a tile (the three counts travel packed in one
-// 64-bit word, 21 bits each), and tiles are chained with decoupled look-back (flag+value packed in one
+// loads), a block-wide scan combines 4096 entries at a time (the three counts travel packed in one
+// 64-bit word, 21 bits each), and the (large) tiles are chained with decoupled look-back (flag+value packed in one
 // 64-bit descriptor per tile and quantity; tile numbers are handed out by an atomic ticket so a tile only
 // ever waits for tiles that started before it).  HBM-bound: 4 bytes in, 12 bytes out per entry.
 #pragma once
@@ -19,7 +19,7 @@
 namespace cub {
 
 constexpr int kScanThreads = 256;
-constexpr int kScanPerThread = 16;
+constexpr int kScanPerThread = 4;   // one 16-byte load per thread: a warp reads / writes 512 contiguous bytes
 constexpr int kScanTile = kScanThreads * kScanPerThread;
 
 constexpr uint64_t kFlagShift = 62;
@@ -37,6 +37,7 @@ struct ScanArgs {
   unsigned plane_lo;             // active corners are counted from this local plane on (ghost plane below: not)
   unsigned long long* status;    // [3][n_tiles] descriptors
   unsigned n_tiles;
+  size_t tile;                   // entries per tile (a multiple of kScanTile)
   unsigned int* ticket;
   unsigned long long* totals;    // [0] vertices, [1] faces, [2] active corners of the scanned range
 };
@@ -73,66 +74,73 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long*
   return exclusive;
 }
 
+// Two passes over a LARGE tile per CTA (args.tile entries, a multiple of kScanTile; a few hundred tiles in all):
+//   pass 1  sums the tile (loads only) -> publishes the aggregate -> look-back gives the tile's exclusive prefix
+//   pass 2  re-reads the tile (L2), block-scans it 4096 entries at a time and writes the three offset arrays.
+// The look-back walks over every tile that is in flight without a finished prefix, so its cost is per TILE, not
+// per byte: with 4096-entry tiles (r1-e) it dominated (0.25 ms for 0.6 GB); one large tile per resident CTA pays
+// it once.
 __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_excl[3];
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // persistent CTAs: few enough tiles are in flight that a look-back finds a finished prefix within a few
-  // descriptors (a grid of one CTA per tile kept ~1200 tiles in flight and walked through all of them)
-  while (true) {
+
   if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
   __syncthreads();
   const int tile = (int)s_tile;
-  if (tile >= (int)a.n_tiles) break;
+  if (tile >= (int)a.n_tiles) return;
+  const size_t t0 = (size_t)tile * a.tile;                       // first entry of the tile, within the range
+  const size_t t1 = t0 + a.tile < a.n ? t0 + a.tile : a.n;
 
-  const size_t g0 = (size_t)tile * kScanTile + (size_t)threadIdx.x * kScanPerThread;  // within the range
-  uint32_t c[kScanPerThread];
-#pragma unroll
-  for (int j = 0; j < kScanPerThread; ++j) c[j] = 0;
-  if (g0 < a.n) {
-    const size_t e = a.e_begin + g0;  // absolute entry index, a multiple of 4 (EW is)
-#pragma unroll
-    for (int v4 = 0; v4 < kScanPerThread / 4; ++v4) {
-      if (g0 + 4 * v4 < a.n) {
-        const uint4 q = __ldg(reinterpret_cast<const uint4*>(a.cnt + e) + v4);
-        // a 4-entry group never straddles planes; active corners below plane_lo belong to the slab underneath
-        const bool ghost = (unsigned)((e + 4 * v4) / a.plane_entries) < a.plane_lo;
-        const uint32_t keep = ghost ? 0xfffffu : 0xffffffffu;
-        c[4 * v4 + 0] = q.x & keep; c[4 * v4 + 1] = q.y & keep; c[4 * v4 + 2] = q.z & keep; c[4 * v4 + 3] = q.w & keep;
-      }
-    }
-  }
   // three 21-bit fields in one 64-bit word: vertices | faces << 21 | active corners << 42
   auto widen = [](uint32_t p) {
     return (unsigned long long)(p & 0x3ffu) | ((unsigned long long)((p >> 10) & 0x3ffu) << 21) |
            ((unsigned long long)(p >> 20) << 42);
   };
-  unsigned long long mine = 0;
+  // 16 consecutive entries of this thread in the 4096-entry block starting at g (masked + zero padded)
+  auto load16 = [&](size_t g, uint32_t (&c)[kScanPerThread]) {
+    const size_t g0 = g + (size_t)threadIdx.x * kScanPerThread;
+    const size_t e = a.e_begin + g0;  // absolute entry index, a multiple of 4 (EW is)
 #pragma unroll
-  for (int j = 0; j < kScanPerThread; ++j) mine += widen(c[j]);
-  unsigned long long incl = mine;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) s_warp[warp] = incl;
-  __syncthreads();
-  unsigned long long warp_excl = 0, block_total = 0;
-#pragma unroll
-  for (int i = 0; i < kScanThreads / 32; ++i) {
-    const unsigned long long t = s_warp[i];
-    if (i < warp) warp_excl += t;
-    block_total += t;
-  }
+    for (int v4 = 0; v4 < kScanPerThread / 4; ++v4) {
+      uint4 q = make_uint4(0, 0, 0, 0);
+      if (g0 + 4 * v4 < t1) {
+        q = __ldg(reinterpret_cast<const uint4*>(a.cnt + e) + v4);
+        // a 4-entry group never straddles planes; active corners below plane_lo belong to the slab underneath
+        const bool ghost = (unsigned)((e + 4 * v4) / a.plane_entries) < a.plane_lo;
+        const uint32_t keep = ghost ? 0xfffffu : 0xffffffffu;
+        q.x &= keep; q.y &= keep; q.z &= keep; q.w &= keep;
+      }
+      c[4 * v4 + 0] = q.x; c[4 * v4 + 1] = q.y; c[4 * v4 + 2] = q.z; c[4 * v4 + 3] = q.w;
+    }
+  };
 
+  // ---- pass 1: tile aggregate (fields can exceed 21 bits over a large tile: three separate sums) ------------
+  unsigned long long sum[3] = {0, 0, 0};
+  for (size_t g = t0; g < t1; g += kScanTile) {
+    uint32_t c[kScanPerThread];
+    load16(g, c);
+    unsigned long long m = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) m += widen(c[j]);
+    sum[0] += m & 0x1fffffull; sum[1] += (m >> 21) & 0x1fffffull; sum[2] += m >> 42;
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum[k] += __shfl_xor_sync(0xffffffffu, sum[k], o);
+  }
+  __shared__ unsigned long long s_part[3][kScanThreads / 32];
+  if (lane == 0) { s_part[0][warp] = sum[0]; s_part[1][warp] = sum[1]; s_part[2][warp] = sum[2]; }
+  __syncthreads();
   if (warp < 3) {
-    // warps 0..2 chain one quantity each, concurrently (three look-backs in a row tripled the tile latency)
+    // warps 0..2 chain one quantity each, concurrently
     const int k = warp;
+    unsigned long long aggk = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) aggk += s_part[k][i];
     unsigned long long* st = a.status + (size_t)k * a.n_tiles;
-    const unsigned long long aggk = (block_total >> (21 * k)) & 0x1fffffull;
     if (lane == 0) st_relaxed(st + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | aggk);
     unsigned long long ex = 0;
     if (tile > 0) {
@@ -141,20 +149,44 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
     }
     if (lane == 0) {
       s_excl[k] = ex;
-      if ((size_t)(tile + 1) * kScanTile >= a.n) a.totals[k] = ex + aggk;  // last tile: grand totals
+      if (tile == (int)a.n_tiles - 1) a.totals[k] = ex + aggk;  // last tile: grand totals
     }
   }
   __syncthreads();
+  unsigned long long run_v = s_excl[0], run_f = s_excl[1], run_k = s_excl[2];
 
-  if (g0 < a.n) {
+  // ---- pass 2: offsets ------------------------------------------------------------------------------------
+  for (size_t g = t0; g < t1; g += kScanTile) {
+    uint32_t c[kScanPerThread];
+    load16(g, c);
+    unsigned long long mine = 0;
+#pragma unroll
+    for (int j = 0; j < kScanPerThread; ++j) mine += widen(c[j]);
+    unsigned long long incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    __syncthreads();  // s_warp of the previous block has been read
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    unsigned long long warp_excl = 0, block_total = 0;
+#pragma unroll
+    for (int i = 0; i < kScanThreads / 32; ++i) {
+      const unsigned long long t = s_warp[i];
+      if (i < warp) warp_excl += t;
+      block_total += t;
+    }
     const unsigned long long excl = warp_excl + (incl - mine);
-    uint32_t v = (uint32_t)(s_excl[0] + (excl & 0x1fffffull));
-    uint32_t f = (uint32_t)(s_excl[1] + ((excl >> 21) & 0x1fffffull));
-    uint32_t k = (uint32_t)(s_excl[2] + (excl >> 42));
+    uint32_t v = (uint32_t)(run_v + (excl & 0x1fffffull));
+    uint32_t f = (uint32_t)(run_f + ((excl >> 21) & 0x1fffffull));
+    uint32_t k = (uint32_t)(run_k + (excl >> 42));
+    const size_t g0 = g + (size_t)threadIdx.x * kScanPerThread;
     const size_t e = a.e_begin + g0;
 #pragma unroll
     for (int v4 = 0; v4 < kScanPerThread / 4; ++v4) {
-      if (g0 + 4 * v4 < a.n) {
+      if (g0 + 4 * v4 < t1) {
         uint4 ov, of, ok;
 #define CUB_STEP(field, j)                                   \
         ov.field = v; of.field = f; ok.field = k;            \
@@ -166,8 +198,7 @@ __global__ void __launch_bounds__(kScanThreads) k_count_scan(const ScanArgs a) {
         reinterpret_cast<uint4*>(a.cofs + e)[v4] = ok;
       }
     }
-  }
-  __syncthreads();  // s_tile / s_warp / s_excl are reused by the next tile
+    run_v += block_total & 0x1fffffull; run_f += (block_total >> 21) & 0x1fffffull; run_k += block_total >> 42;
   }
 }
 
