@@ -354,7 +354,27 @@ def main():
         ms_e, _, _ = timed(e2e_step, max(2, min(args.steps, 5)), 1)
         e2e = {"value": voxels_total / (ms_e * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms_e,
                "h2d_bytes_per_step": int(vol_host.numel() * 4), "d2h_bytes_per_step": int(n_pts * 12 + n_quads * 16),
-               "mfaces_per_s": tot[1] / (ms_e * 1e-3) / 1e6}
+               "mfaces_per_s": tot[1] / (ms_e * 1e-3) / 1e6, "mode": "one slab per GPU: copy in, run, copy out"}
+        if N == 1:
+            # streamed: the volume travels through 3 handles (3 streams) as 16 z-slabs, so the PCIe copies in both
+            # directions and the kernels overlap (slabs.run_streamed: the same public calls, ids stay global)
+            hs = [capi.Handle(local_rank) for _ in range(3)]
+
+            def e2e_streamed():
+                a, b = P.slabs.run_streamed(hs, vol_host.data_ptr(), np.float32, (S, S, hi - lo), prm, 16,
+                                            pts_host.data_ptr(), cells_host.data_ptr())
+                assert (a, b) == (n_pts, n_quads)
+                return a, b, None
+
+            ms_s, _, _ = timed(e2e_streamed, max(2, min(args.steps, 5)), 1)
+            for x in hs:
+                x.close()
+            unstreamed = e2e
+            e2e = {"value": voxels_total / (ms_s * 1e-3) / 1e9, "unit": "Gvoxels/s", "ms_per_step": ms_s,
+                   "h2d_bytes_per_step": int(vol_host.numel() * 4 * (1 + 4 * 15 / (hi - lo))),
+                   "d2h_bytes_per_step": int(n_pts * 12 + n_quads * 16), "mfaces_per_s": tot[1] / (ms_s * 1e-3) / 1e6,
+                   "mode": "streamed: 16 z-slabs through 3 handles / streams (2-slice halos re-sent)",
+                   "unstreamed": unstreamed}
         he.close()
         del vol_host
 

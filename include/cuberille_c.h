@@ -152,6 +152,15 @@ int cub_run(cub_handle h, const cub_params *p, int id_bytes,
  *   mem_kind  : where those three buffers live                                 */
 int cub_fetch(cub_handle h, float *points, void *cells, void *cell_data, int mem_kind);
 
+/* cub_fetch without the final synchronisation: the copies are only ordered on the
+ * handle's stream; call cub_synchronize before reading the destination buffers.
+ * Lets a caller that streams z-slabs through several handles overlap the
+ * device->host copy of one slab with the host->device copy of the next.        */
+int cub_fetch_async(cub_handle h, float *points, void *cells, void *cell_data, int mem_kind);
+
+/* Blocks until everything issued on the handle's stream has finished.          */
+int cub_synchronize(cub_handle h);
+
 /* Zero-copy access to the result buffers on the device (valid until the next
  * cub_count on this handle).  Any out pointer may be NULL.                     */
 int cub_device_buffers(cub_handle h, const float **points, const void **cells,

@@ -26,7 +26,8 @@ CODE_DTYPES = {v: k for k, v in DTYPE_CODES.items()}
 # every symbol include/cuberille_c.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "cub_abi_version", "cub_default_params", "cub_create", "cub_destroy", "cub_last_error", "cub_set_volume",
-    "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit", "cub_run", "cub_fetch", "cub_device_buffers",
+    "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
+    "cub_synchronize", "cub_device_buffers",
     "cub_debug_bitmask", "cub_debug_project_points", "cub_generate_volume", "cub_download_volume",
     "cub_enable_timing", "cub_get_timings", "cub_launch_count",
 ]
@@ -93,6 +94,10 @@ def load() -> C.CDLL:
     L.cub_run.argtypes = [vp, C.POINTER(Params), i, pu64, pu64]
     L.cub_fetch.restype = i
     L.cub_fetch.argtypes = [vp, vp, vp, vp, i]
+    L.cub_fetch_async.restype = i
+    L.cub_fetch_async.argtypes = [vp, vp, vp, vp, i]
+    L.cub_synchronize.restype = i
+    L.cub_synchronize.argtypes = [vp]
     L.cub_device_buffers.restype = i
     L.cub_device_buffers.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), pu64, pu64, C.POINTER(i), C.POINTER(i)]
     L.cub_debug_bitmask.restype = i
@@ -220,8 +225,12 @@ class Handle:
                                       cd.ctypes.data if cd is not None else None, MEM_HOST))
         return pts, cells, cd
 
-    def fetch_into(self, points_ptr: int, cells_ptr: int, cell_data_ptr: int = 0, mem_kind: int = MEM_HOST):
-        self._check(self._L.cub_fetch(self._h, C.c_void_p(points_ptr) if points_ptr else None,
+    def synchronize(self):
+        self._check(self._L.cub_synchronize(self._h))
+
+    def fetch_into(self, points_ptr: int, cells_ptr: int, cell_data_ptr: int = 0, mem_kind: int = MEM_HOST, sync: bool = True):
+        fn = self._L.cub_fetch if sync else self._L.cub_fetch_async
+        self._check(fn(self._h, C.c_void_p(points_ptr) if points_ptr else None,
                                       C.c_void_p(cells_ptr) if cells_ptr else None,
                                       C.c_void_p(cell_data_ptr) if cell_data_ptr else None, mem_kind))
 

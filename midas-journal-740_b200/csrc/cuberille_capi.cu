@@ -60,7 +60,7 @@ int tuning_knob(const char* name, int dflt) {
 template <int MODE>
 cudaError_t dispatch_sweep(const SweepArgs& a, cudaStream_t st) {
   // wide tiles (16 voxel words per row) for big volumes, narrow ones (8) when a row has few words
-  const int cfg = tuning_knob(MODE == MODE_COUNT ? "CUB_COUNT_CFG" : "CUB_ASSIGN_CFG", a.g.Wx > 8 ? 1 : 10);
+  const int cfg = tuning_knob(MODE == MODE_COUNT ? "CUB_COUNT_CFG" : "CUB_ASSIGN_CFG", a.g.Wx > 8 ? 2 : 10);
   switch (cfg) {
     case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE>>(a, st);
     case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE>>(a, st);
@@ -704,7 +704,7 @@ int cub_run(cub_handle h, const cub_params* p, int id_bytes, uint64_t* n_points,
   return CUB_OK;
 }
 
-int cub_fetch(cub_handle h, float* points, void* cells, void* cell_data, int mem_kind) {
+int cub_fetch_async(cub_handle h, float* points, void* cells, void* cell_data, int mem_kind) {
   if (!h) return CUB_ERR_INVALID;
   if (!h->emitted) return fail(h, CUB_ERR_INVALID, "cub_fetch before cub_emit");
   CU_TRY(h, cudaSetDevice(h->device));
@@ -717,8 +717,19 @@ int cub_fetch(cub_handle h, float* points, void* cells, void* cell_data, int mem
     if (!h->params.save_pixel_as_cell_data) return fail(h, CUB_ERR_INVALID, "cell data was not requested");
     CU_TRY(h, cudaMemcpyAsync(cell_data, h->celldata.p, (size_t)h->n_cells * h->pix_bytes, k, h->stream));
   }
+  return CUB_OK;
+}
+
+int cub_synchronize(cub_handle h) {
+  if (!h) return CUB_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return CUB_OK;
+}
+
+int cub_fetch(cub_handle h, float* points, void* cells, void* cell_data, int mem_kind) {
+  CUB_TRY(cub_fetch_async(h, points, cells, cell_data, mem_kind));
+  return cub_synchronize(h);
 }
 
 int cub_device_buffers(cub_handle h, const float** points, const void** cells, const void** cell_data,

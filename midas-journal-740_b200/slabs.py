@@ -53,3 +53,43 @@ def all_gather_counts(n_points: int, n_cells: int, device=None) -> list[tuple[in
     dist.all_gather_into_tensor(out, mine)
     flat = out.cpu().tolist()
     return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
+
+
+def run_streamed(handles, vol_ptr: int, dtype, dims_xyz, params, n_slabs: int, out_points_ptr: int, out_cells_ptr: int,
+                 id_bytes: int = 4, halo: int = 2, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+    """One GPU, host volume in, host mesh out, streamed: the image is cut into `n_slabs` z-slabs that travel
+    through `handles` (>= 2 capi.Handle objects, each on its own stream) round-robin, so the host->device copy
+    of slab c+1, the kernels of slab c and the device->host copy of slab c-1 overlap.  Ids are global: the id
+    base of a slab is the running sum of the counts of the slabs before it (the same exclusive scan the
+    multi-GPU path gets from its all-gather).  `vol_ptr` / `out_*_ptr`: pinned host memory; the outputs must
+    be large enough for the whole mesh.  Returns (n_points, n_cells)."""
+    import numpy as np
+    from . import capi
+    nx, ny, nz = dims_xyz
+    item = np.dtype(dtype).itemsize
+    slabs = plan_slabs(nz, n_slabs, halo)
+    verts_per_cell = 3 if params.generate_triangles else 4
+    cells_per_quad = 2 if params.generate_triangles else 1
+    pbase = cbase = 0
+
+    def upload(c):
+        s, h = slabs[c], handles[c % len(handles)]
+        h.set_volume_ptr(vol_ptr + s.local_z0 * ny * nx * item, dtype, (nx, ny, s.local_z1 - s.local_z0), capi.MEM_HOST,
+                         spacing, origin)
+        h.set_slab(nz, s.local_z0, s.own_z0, s.own_z1)
+
+    upload(0)
+    for c in range(n_slabs):
+        h = handles[c % len(handles)]
+        if c + 1 < n_slabs:
+            upload(c + 1)             # queued on the next handle's stream before this slab's count blocks the host
+        n_pts, n_quads = h.count(params)
+        h.set_id_base(pbase, cbase)
+        h.emit(id_bytes)
+        h.fetch_into(out_points_ptr + pbase * 12, out_cells_ptr + cbase * verts_per_cell * id_bytes, 0, capi.MEM_HOST,
+                     sync=False)
+        pbase += n_pts
+        cbase += n_quads * cells_per_quad
+    for h in handles:
+        h.synchronize()
+    return pbase, cbase
