@@ -96,7 +96,8 @@ struct cub_handle_s {
 
   // scratch
   DevBuf<uint32_t> bits, cnt, act, vofs, fofs, cofs, perm;
-  DevBuf<uint2> vtx;
+  DevBuf<uint32_t> vtx;
+  DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
   uint64_t ent_layout[3] = {0, 0, 0};
   int EY = 0, EW = 0;
   uint64_t n_active = 0, ghost_c = 0;   // active corners of the scanned planes / of the bottom plane (slab below owns them)
@@ -343,7 +344,7 @@ int cub_destroy(cub_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
-  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
+  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->vsl.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
   cudaFree(h->d_ticket); cudaFree(h->d_totals);
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
@@ -444,7 +445,7 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   if ((unsigned long long)g.Y * g.Zl * ((g.Wx + kWordsPerTask - 1) / kWordsPerTask) >= (1ull << 32))
     return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
   if ((unsigned long long)g.Y * g.Wp >= (1ull << 31)) return fail(h, CUB_ERR_UNSUPPORTED, "x*y too large");
-  if (g.X > 65534 || g.Y > 65534) return fail(h, CUB_ERR_UNSUPPORTED, "x / y size above 65534 voxels is not supported");
+  if (g.X > 65534 || g.Y > 32766) return fail(h, CUB_ERR_UNSUPPORTED, "x size above 65534 or y size above 32766 voxels is not supported");
   const size_t words = (size_t)g.Zl * g.Y * g.Wp;
   const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
                               h->bits_layout[2] != (uint64_t)g.Zl;
@@ -602,6 +603,7 @@ int cub_emit(cub_handle h, int id_bytes) {
   CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
   if (!h->raster) {
     CUB_TRY(ensure(h, h->vtx, n_pts_all));
+    CUB_TRY(ensure(h, h->vsl, (size_t)(h->zs1 - h->owner_z_min) + 1 + (n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds));
     CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
   }
   if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
@@ -624,12 +626,21 @@ int cub_emit(cub_handle h, int id_bytes) {
       }
       {
         // K3b: points + corner -> id map
+        const int nz = h->zs1 - h->owner_z_min;
+        const unsigned n_blocks = (unsigned)((n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds);
+        SliceIndexArgs si{};
+        si.vofs = h->vofs.p; si.plane_entries = (size_t)h->EY * h->EW; si.z_first = h->owner_z_min; si.nz = nz;
+        si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
+        const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
+        k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
+        h->launches++;
         VertexArgs a{};
         a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
+        a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
         a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
         a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
         a.points = h->points.p; a.perm = h->perm.p;
-        k_vertices<<<(unsigned)((n_pts_all + 255) / 256), 256, 0, h->stream>>>(a);
+        k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
         h->launches++;
         CU_TRY(h, cudaGetLastError());
       }

@@ -46,7 +46,8 @@ struct SweepArgs {
   uint32_t* act;       // [Zl+1][EY][EW] active-corner mask of the corner word
   // --- assign
   const uint32_t* vofs;      // [Zl+1][EY][EW] exclusive scan of the owned-corner counts
-  uint2* vtx;                // [n vertices] x = cx | cy << 16, y = local corner plane
+  uint32_t* vtx;             // [n vertices] cx | cy << 16 | oz << 31  (oz: the corner is on the owner slice's upper plane;
+                             //  the owner slice follows from the id: ids of a slice are contiguous, k_vertices.cuh)
 };
 
 template <int NTX_, int NTY_, int R_, int MODE_>
@@ -316,22 +317,22 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
           assemble(k, O);
           uint32_t U = O[0] | O[1] | O[2] | O[3] | O[4] | O[5] | O[6] | O[7];
           if (U) {
-            uint2* __restrict__ out = a.vtx + vpre[k];
+            uint32_t* __restrict__ const out = a.vtx;
+            uint32_t n = vpre[k];   // a 32-bit index: a predicated 64-bit pointer bump costs 6 instructions here
             const uint32_t xy0 = (uint32_t)(cw * 32) | ((uint32_t)(cy0 + k) << 16);
-            const uint32_t pz0 = (uint32_t)z, pz1 = (uint32_t)z + 1u;
             while (U) {
               const int b = __ffs(U) - 1;
               U &= U - 1;
               const uint32_t bit = 1u << b;
               const uint32_t xy = xy0 + (uint32_t)b;
-              if (O[0] & bit) { *out++ = make_uint2(xy, pz0); }
-              if (O[1] & bit) { *out++ = make_uint2(xy + 1u, pz0); }
-              if (O[2] & bit) { *out++ = make_uint2(xy + 0x10001u, pz0); }
-              if (O[3] & bit) { *out++ = make_uint2(xy + 0x10000u, pz0); }
-              if (O[4] & bit) { *out++ = make_uint2(xy, pz1); }
-              if (O[5] & bit) { *out++ = make_uint2(xy + 1u, pz1); }
-              if (O[6] & bit) { *out++ = make_uint2(xy + 0x10001u, pz1); }
-              if (O[7] & bit) { *out++ = make_uint2(xy + 0x10000u, pz1); }
+              if (O[0] & bit) { out[n] = xy; ++n; }
+              if (O[1] & bit) { out[n] = xy + 1u; ++n; }
+              if (O[2] & bit) { out[n] = xy + 0x10001u; ++n; }
+              if (O[3] & bit) { out[n] = xy + 0x10000u; ++n; }
+              if (O[4] & bit) { out[n] = xy + 0x80000000u; ++n; }
+              if (O[5] & bit) { out[n] = xy + 0x80000001u; ++n; }
+              if (O[6] & bit) { out[n] = xy + 0x80010001u; ++n; }
+              if (O[7] & bit) { out[n] = xy + 0x80010000u; ++n; }
             }
           }
         }
