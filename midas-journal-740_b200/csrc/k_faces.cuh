@@ -33,7 +33,7 @@ struct FaceArgs {
 };
 
 template <typename IdT, int MODE>
-__device__ __forceinline__ void write_cell(const FaceArgs& a, size_t fidx, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+__device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
   if (MODE == kEmitScratchQuads) {
     reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4(q0, q1, q2, q3);
     return;
@@ -41,7 +41,7 @@ __device__ __forceinline__ void write_cell(const FaceArgs& a, size_t fidx, uint3
   const IdT v0 = (IdT)(q0 + a.id_delta), v1 = (IdT)(q1 + a.id_delta), v2 = (IdT)(q2 + a.id_delta), v3 = (IdT)(q3 + a.id_delta);
   IdT* c = reinterpret_cast<IdT*>(a.cells);
   if (MODE == kEmitQuads) {
-    c += fidx * 4;
+    c += (size_t)fidx * 4;
     if (sizeof(IdT) == 4) {
       *reinterpret_cast<uint4*>(c) = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, (uint32_t)v3);
     } else {
@@ -49,7 +49,7 @@ __device__ __forceinline__ void write_cell(const FaceArgs& a, size_t fidx, uint3
     }
   } else {
     // unprojected quad: both diagonals are equal, `>=` takes the first split (txx:298-302)
-    c += fidx * 6;
+    c += (size_t)fidx * 6;
     c[0] = v0; c[1] = v1; c[2] = v3;
     c[3] = v1; c[4] = v2; c[5] = v3;
   }
@@ -86,7 +86,6 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t slice_words = (size_t)g.Y * g.Wp;
   // grid: x = 32-word segments of a row, y = groups of 8 rows (one row per warp), z = own slices
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kFaceThreads / 32) + warp, zl = a.z_begin + blockIdx.z;
 
@@ -94,7 +93,8 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
   uint32_t F[6] = {0, 0, 0, 0, 0, 0};
   {
     if (w < g.Wx && y < g.Y) {
-      const uint32_t* __restrict__ row = a.bits + ((size_t)zl * g.Y + y) * g.Wp + w;
+      // word and entry indices fit 32 bits (cub_count checks the lattice size): one IMAD.WIDE per load
+      const uint32_t* __restrict__ row = a.bits + (((uint32_t)zl * (uint32_t)g.Y + (uint32_t)y) * (uint32_t)g.Wp + (uint32_t)w);
       const uint32_t c0 = __ldg(row);
       const uint32_t XB = g.X & 31;
       const uint32_t vc = (w == g.Wx - 1 && XB) ? ((1u << XB) - 1u) : ~0u;
@@ -130,16 +130,14 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
   if (U) {
     // ---- context of the word: the corner words around it ------------------------------------------------
     const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
-    const size_t e00 = ((size_t)zl * a.EY + y) * a.EW + w;  // corner word (w, y, z)
-    const uint32_t* __restrict__ ap = a.act + e00;
-    const uint32_t* __restrict__ cp = a.cofs + e00;
+    const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
     uint32_t A[4], C[4], Cn[4];                              // index oz*2+oy
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int d = (k >> 1) * plane + (k & 1) * a.EW;
-      A[k] = __ldg(ap + d);
-      C[k] = __ldg(cp + d);
-      Cn[k] = __ldg(cp + d + 1);
+      const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
+      A[k] = __ldg(a.act + e);
+      C[k] = __ldg(a.cofs + e);
+      Cn[k] = __ldg(a.cofs + e + 1u);
     }
     uint4* cx = sm.ctx[warp][lane];
     cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
@@ -168,7 +166,7 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
     const uint32_t Fm[6] = {Fa.x, Fa.y, Fa.z, Fa.w, Fb.x, Fb.y};
     const uint32_t bit = 1u << b, below = bit - 1u;
     // index of the voxel's first face: faces of the voxels before it in the word
-    size_t fi = Fb.z;
+    uint32_t fi = Fb.z;  // faces of a handle < 2^32 (cub_count)
 #pragma unroll
     for (int f = 0; f < 6; ++f) fi += __popc(Fm[f] & below);
     // slots of the 8 corners of voxel b; local l -> (ox, oy, oz) as in txx:236-254
