@@ -91,29 +91,56 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
 
   // ---- face masks of the word (txx:164-173; clamped neighbours: no face on the image border) --------------
   uint32_t F[6] = {0, 0, 0, 0, 0, 0};
+  // context of the word: active masks and slot bases of the 4 corner words around it (index oz*2+oy), the slot
+  // bases of the corner words at w+1 (the next lane's, except at the end of the segment), first face index
+  const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
+  const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
+  uint32_t A[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0}, Cn[4] = {0, 0, 0, 0}, fbase = 0;
   {
-    if (w < g.Wx && y < g.Y) {
-      // word and entry indices fit 32 bits (cub_count checks the lattice size): one IMAD.WIDE per load
-      const uint32_t* __restrict__ row = a.bits + (((uint32_t)zl * (uint32_t)g.Y + (uint32_t)y) * (uint32_t)g.Wp + (uint32_t)w);
-      const uint32_t c0 = __ldg(row);
+    // all the words are requested together (no early-out on an empty word: that would make the neighbour
+    // loads wait for the first one, and the kernel is bound by its chain of dependent loads)
+    const bool valid = w < g.Wx && y < g.Y;
+    // word and entry indices fit 32 bits (cub_count checks the lattice size): one IMAD.WIDE per load
+    const uint32_t* __restrict__ row = a.bits + (((uint32_t)zl * (uint32_t)g.Y + (uint32_t)y) * (uint32_t)g.Wp + (uint32_t)w);
+    const int zgl = zl + g.zg0;
+    const int sw = g.Y * g.Wp;  // words per slice (< 2^31: checked by cub_count)
+    // neighbour rows / slices as signed word offsets from `row` (0 = clamped onto the row itself)
+    const int dym = (y > 0) ? -g.Wp : 0, dyp = (y < g.Y - 1) ? g.Wp : 0;
+    const int dzm = (zgl > 0 && zl > 0) ? -sw : 0, dzp = (zgl < g.Zg - 1 && zl < g.Zl - 1) ? sw : 0;
+    uint32_t c0 = 0, nym = 0, nyp = 0, nzm = 0, nzp = 0, edge = 0;
+    if (valid) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
+        A[k] = __ldg(a.act + e);
+        C[k] = __ldg(a.cofs + e);
+        if (lane == 31) Cn[k] = __ldg(a.cofs + e + 1u);
+      }
+      fbase = __ldg(a.fofs + e00);
+      c0 = __ldg(row);
+      nym = __ldg(row + dym); nyp = __ldg(row + dyp); nzm = __ldg(row + dzm); nzp = __ldg(row + dzp);
+      // the x neighbours are the adjacent lanes' words, except across the ends of the warp's 32-word segment
+      if (lane == 0 && w > 0) edge = __ldg(row - 1);
+      if (lane == 31 && w < g.Wx - 1) edge = __ldg(row + 1);
+    }
+    const uint32_t up = __shfl_up_sync(0xffffffffu, c0, 1), dn = __shfl_down_sync(0xffffffffu, c0, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t nx = __shfl_down_sync(0xffffffffu, C[k], 1);
+      if (lane != 31) Cn[k] = nx;
+    }
+    if (valid) {
       const uint32_t XB = g.X & 31;
       const uint32_t vc = (w == g.Wx - 1 && XB) ? ((1u << XB) - 1u) : ~0u;
       const uint32_t c = c0 & vc;
-      if (c) {
-        // neighbour rows / slices as signed word offsets from `row` (0 = clamped onto the row itself)
-        const int zgl = zl + g.zg0;
-        const int sw = g.Y * g.Wp;  // words per slice (< 2^31: checked by cub_count)
-        const int dym = (y > 0) ? -g.Wp : 0, dyp = (y < g.Y - 1) ? g.Wp : 0;
-        const int dzm = (zgl > 0 && zl > 0) ? -sw : 0, dzp = (zgl < g.Zg - 1 && zl < g.Zl - 1) ? sw : 0;
-        const uint32_t prev = (w == 0) ? (c0 << 31) : __ldg(row - 1);
-        const uint32_t next = (w == g.Wx - 1) ? (c0 >> 31) : __ldg(row + 1);
-        F[0] = c & ~__funnelshift_l(prev, c0, 1);
-        F[1] = c & ~__ldg(row + dym);
-        F[2] = c & ~__funnelshift_r(c0, next, 1);
-        F[3] = c & ~__ldg(row + dyp);
-        F[4] = c & ~__ldg(row + dzm);
-        F[5] = c & ~__ldg(row + dzp);
-      }
+      const uint32_t prev = (w == 0) ? (c0 << 31) : (lane == 0 ? edge : up);
+      const uint32_t next = (w == g.Wx - 1) ? (c0 >> 31) : (lane == 31 ? edge : dn);
+      F[0] = c & ~__funnelshift_l(prev, c0, 1);
+      F[1] = c & ~nym;
+      F[2] = c & ~__funnelshift_r(c0, next, 1);
+      F[3] = c & ~nyp;
+      F[4] = c & ~nzm;
+      F[5] = c & ~nzp;
     }
   }
   uint32_t U = F[0] | F[1] | F[2] | F[3] | F[4] | F[5];
@@ -128,23 +155,12 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
   if (total == 0) return;  // most warps: no surface voxel in 1024 voxels
 
   if (U) {
-    // ---- context of the word: the corner words around it ------------------------------------------------
-    const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
-    const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
-    uint32_t A[4], C[4], Cn[4];                              // index oz*2+oy
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
-      A[k] = __ldg(a.act + e);
-      C[k] = __ldg(a.cofs + e);
-      Cn[k] = __ldg(a.cofs + e + 1u);
-    }
     uint4* cx = sm.ctx[warp][lane];
     cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
     cx[1] = make_uint4(C[0], C[1], C[2], C[3]);
     cx[2] = make_uint4(Cn[0], Cn[1], Cn[2], Cn[3]);
     cx[3] = make_uint4(F[0], F[1], F[2], F[3]);
-    cx[4] = make_uint4(F[4], F[5], __ldg(a.fofs + e00) - a.ghost_f, 0u);
+    cx[4] = make_uint4(F[4], F[5], fbase - a.ghost_f, 0u);
     if (a.celldata) sm.vox0[warp][lane] = ((unsigned long long)zl * g.Y + y) * g.X + (unsigned long long)w * 32;
     uint32_t pos = incl - nvox;
     uint16_t* q = sm.queue[warp];
