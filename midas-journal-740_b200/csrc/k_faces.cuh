@@ -74,7 +74,6 @@ constexpr int kFaceThreads = 256;
 //   [2] Cn[oz][oy]  slot bases of the corner words at w+1     [3] F0..F3     [4] F4, F5, face base, -
 struct FaceSmem {
   uint4 ctx[kFaceThreads / 32][32][5];
-  unsigned long long vox0[kFaceThreads / 32][32];  // index of the word's voxel 0 in the volume (cell data)
   uint16_t queue[kFaceThreads / 32][1024];         // (lane << 5) | bit of every surface voxel of the warp's words
 };
 
@@ -82,7 +81,7 @@ struct FaceSmem {
 // compacted into a queue and handled one per lane, so a word with ten surface voxels does not stall the 31
 // lanes whose words have none.
 template <typename IdT, int MODE>
-__global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
+__global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -161,7 +160,6 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
     cx[2] = make_uint4(Cn[0], Cn[1], Cn[2], Cn[3]);
     cx[3] = make_uint4(F[0], F[1], F[2], F[3]);
     cx[4] = make_uint4(F[4], F[5], fbase - a.ghost_f, 0u);
-    if (a.celldata) sm.vox0[warp][lane] = ((unsigned long long)zl * g.Y + y) * g.X + (unsigned long long)w * 32;
     uint32_t pos = incl - nvox;
     uint16_t* q = sm.queue[warp];
     const uint32_t tag = (uint32_t)lane << 5;
@@ -204,7 +202,8 @@ __global__ void __launch_bounds__(kFaceThreads) k_faces(const FaceArgs a) {
       for (int l = 0; l < 8; ++l)
         if (need[l]) vid[l] = __ldg(a.perm + vid[l]);
     }
-    const size_t voxel = a.celldata ? (size_t)(sm.vox0[warp][src] + b) : 0;
+    // the voxel behind the face (cell data): word src of this warp's row
+    const size_t voxel = a.celldata ? ((size_t)zl * g.Y + y) * g.X + (size_t)(blockIdx.x * 32 + src) * 32 + b : 0;
     if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
