@@ -112,9 +112,10 @@ int cub_set_volume(cub_handle h, const void *data, int dtype, const uint64_t dim
  *   image_nz      : z size of the WHOLE image
  *   local_z0      : global z index of the local buffer's slice 0
  *   own_z0/own_z1 : global half-open z range whose voxels this handle emits
- * The local buffer must contain slices [own_z0-2, own_z1+2) clipped to the
- * image (2-slice halo: one for face/corner classification, one so that the
- * first-touch owner of a shared corner is computed identically on both sides);
+ * The local buffer must contain slices [own_z0-2, own_z1+1) clipped to the
+ * image (2 slices below: one for face/corner classification, one so that the
+ * first-touch owner of a shared corner is computed identically on both sides;
+ * 1 slice above for the +z faces; more is harmless);
  * with projection the halo should be >= 8 slices (vertex travel).  Default
  * (never called): the buffer is the whole image.                               */
 int cub_set_slab(cub_handle h, uint64_t image_nz, uint64_t local_z0,
