@@ -429,4 +429,13 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    # stdout carries exactly ONE line, the JSON result: anything a library prints there meanwhile (NCCL's version
+    # banner, for one) is sent to stderr instead
+    sys.stdout.flush()
+    _stdout_fd = os.dup(1)
+    os.dup2(2, 1)
+    _result = sys.stdout = os.fdopen(_stdout_fd, "w")
+    try:
+        main()
+    finally:
+        _result.flush()
