@@ -10,5 +10,5 @@ The C++ drop-in adapter lives in include/itkCuberilleImageToMeshFilter.h.
 """
 from . import capi, mha, slabs  # noqa: F401
 from ._build import build  # noqa: F401
-from .filter import CuberilleImageToMeshFilter, Mesh  # noqa: F401
+from .filter import CuberilleImageToMeshFilter, LinearInterpolateImageFunction, Mesh  # noqa: F401
 from .mha import Image, read_mha, write_mha, write_vtk_polydata  # noqa: F401

@@ -34,6 +34,10 @@ def _clamp(v, lo, hi):
     return lo if v < lo else (hi if v > hi else v)
 
 
+class LinearInterpolateImageFunction:
+    """Marker for the default TInterpolator (h:110): trilinear, what k_project implements."""
+
+
 class CuberilleImageToMeshFilter:
     def __init__(self, device: int = 0, stream: int | None = None, id_bytes: int = 4):
         self._handle = capi.Handle(device, stream)
@@ -51,6 +55,7 @@ class CuberilleImageToMeshFilter:
         self._step = -1.0
         self._relax = 0.95
         self._max_steps = 50
+        self._interpolator = LinearInterpolateImageFunction()
 
     @classmethod
     def New(cls, **kw):
@@ -65,6 +70,17 @@ class CuberilleImageToMeshFilter:
     def SetInput(self, image: Image):
         self._image = image
         self._modified = True
+
+    def SetInterpolator(self, interpolator):
+        """h:187-188.  The GPU path implements the default trilinear interpolation only
+        (LinearInterpolateImageFunction, txx:87-91): anything else is rejected, as in the C++ adapter."""
+        if interpolator is not None and not isinstance(interpolator, LinearInterpolateImageFunction):
+            raise TypeError("only LinearInterpolateImageFunction is supported by the B200 path")
+        self._interpolator = interpolator or LinearInterpolateImageFunction()
+        self._modified = True
+
+    def GetInterpolator(self):
+        return self._interpolator
 
     def SetIsoSurfaceValue(self, v): self._set("_iso", v)
     def GetIsoSurfaceValue(self): return self._iso

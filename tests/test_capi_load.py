@@ -68,3 +68,8 @@ def test_filter_mirror_defaults_and_clamps():
     assert f.GetProjectVertexSurfaceDistanceThreshold() == 0.0
     f.GenerateTriangleFacesOff()
     assert f.GetGenerateTriangleFaces() is False and f._modified
+    # h:187-188: only the default (trilinear) interpolator exists on the GPU path
+    f.SetInterpolator(P.LinearInterpolateImageFunction())
+    assert isinstance(f.GetInterpolator(), P.LinearInterpolateImageFunction)
+    with pytest.raises(TypeError):
+        f.SetInterpolator(object())
