@@ -224,6 +224,32 @@ struct Timer {
 };
 
 // K1 on the local slices [z0, z1) (rows are independent), on `stream`, with at most ctas_per_sm resident CTAs
+template <typename T> struct is_packable { static constexpr bool value = false; };
+template <> struct is_packable<uint8_t> { static constexpr bool value = true; };
+template <> struct is_packable<int8_t> { static constexpr bool value = true; };
+template <> struct is_packable<uint16_t> { static constexpr bool value = true; };
+template <> struct is_packable<int16_t> { static constexpr bool value = true; };
+
+template <typename T, bool PACK = is_packable<T>::value>
+struct ClassifyPacked {
+  static bool launch(cub_handle, const T*, uint32_t*, const Grid&, unsigned long long, unsigned long long, cudaStream_t) { return false; }
+};
+template <typename T>
+struct ClassifyPacked<T, true> {
+  // 4 bytes per lane per load (k_classify_packed): rows must be whole warp loads and the buffer 4-byte aligned
+  static bool launch(cub_handle h, const T* vol, uint32_t* bits, const Grid& g, unsigned long long rows,
+                     unsigned long long max_blocks, cudaStream_t stream) {
+    constexpr int vpl = 4 / (int)sizeof(T);
+    if (g.X % (32 * vpl) != 0 || (reinterpret_cast<uintptr_t>(vol) & 3u) != 0 || tuning_knob("CUB_K1_PACKED", 1) == 0) return false;
+    const unsigned tasks_per_row = (unsigned)((g.Wx + 31) / 32);
+    const unsigned long long tasks = rows * tasks_per_row;  // cub_count checks rows * groups < 2^32
+    unsigned long long blocks = std::min<unsigned long long>((tasks + 7) / 8, max_blocks);
+    if (blocks < 1) blocks = 1;
+    k_classify_packed<T><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, (unsigned)tasks, tasks_per_row);
+    return true;
+  }
+};
+
 template <typename T>
 void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas_per_sm) {
   Grid g = h->g;
@@ -237,11 +263,12 @@ void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas
   const bool full = (g.X % 32 == 0) && (g.Wx % kWordsPerTask == 0);
   const T* vol = static_cast<const T*>(h->d_vol) + (size_t)z0 * g.Y * g.X;
   uint32_t* bits = h->bits.p + (size_t)z0 * g.Y * g.Wp;
+  h->launches++;
+  if (ClassifyPacked<T>::launch(h, vol, bits, g, rows, max_blocks, stream)) return;
   if (full)
     k_classify<T, true><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
   else
     k_classify<T, false><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
-  h->launches++;
 }
 
 int launch_project(cub_handle h, float* pts, size_t n) {

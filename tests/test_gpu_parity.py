@@ -22,7 +22,10 @@ def test_reference_known_answers_on_gpu(row):
 
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64])
-@pytest.mark.parametrize("shape", [(7, 9, 33), (5, 6, 1), (3, 1, 70), (1, 8, 8), (6, 5, 32), (4, 4, 31), (9, 13, 131)])
+# the last five shapes have whole-warp-load rows: 1- and 2-byte pixels take the packed kernel there (one, several
+# and partial 32-word tasks per row)
+@pytest.mark.parametrize("shape", [(7, 9, 33), (5, 6, 1), (3, 1, 70), (1, 8, 8), (6, 5, 32), (4, 4, 31), (9, 13, 131),
+                                   (3, 5, 128), (2, 3, 64), (2, 2, 1152), (1, 2, 192), (2, 1, 2176)])
 def test_bitmask_matches_oracle(dtype, shape):
     """K1: inside == !(v < iso) for every pixel type and ragged row lengths"""
     P, O = pkg(), oracle()
