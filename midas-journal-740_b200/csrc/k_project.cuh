@@ -130,13 +130,70 @@ __global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
     }
     if (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2]) {
       cell[0] = base[0]; cell[1] = base[1]; cell[2] = base[2];
+      const long long zl0 = base[2] - v.zg0;  // local slice of node z = 0
+      const bool nodes_inside = base[0] >= 0 && base[0] + 1 <= v.X - 1 && base[1] >= 0 && base[1] + 1 <= v.Y - 1 &&
+                                base[2] >= 0 && base[2] + 1 <= v.Zg - 1 && zl0 >= 0 && zl0 + 1 <= v.Zl - 1;
+      if (nodes_inside) {
+        // The 8 nodes are in the image, so only their outward 6-neighbours can clamp, and clamp(node +- 1) is the
+        // node itself there.  The nodes and their 6-neighbours are 32 distinct voxels (a 4x2x2 block along each
+        // axis sharing the 2x2x2 nodes), fetched once from 12 row pointers.  Same values and the same arithmetic
+        // as the general path below (which remains for vertices that have left the image).
+        const T* __restrict__ p = v.d + ((size_t)zl0 * v.Y + (size_t)base[1]) * v.X + (size_t)base[0];
+        const ptrdiff_t sx = (ptrdiff_t)v.X, sxy = (ptrdiff_t)v.X * v.Y;
+        const ptrdiff_t xm = base[0] >= 1 ? -1 : 0, xp = base[0] + 2 <= v.X - 1 ? 2 : 1;
+        const ptrdiff_t ym = base[1] >= 1 ? -sx : 0, yp = base[1] + 2 <= v.Y - 1 ? 2 * sx : sx;
+        const ptrdiff_t zm = (base[2] >= 1 && zl0 >= 1) ? -sxy : 0;
+        const ptrdiff_t zp = (base[2] + 2 <= v.Zg - 1 && zl0 + 2 <= v.Zl - 1) ? 2 * sxy : sxy;
+        float ax[2][2][4], ay[2][2][2], az[2][2][2];  // [oz][oy][x = -1..2], [oz][y = -1 | 2][ox], [z = -1 | 2][oy][ox]
 #pragma unroll
-      for (int counter = 0; counter < 8; ++counter) {
-        const int cx = clampi(base[0] + ((counter & 1) ? 1 : 0), v.X - 1);
-        const int cy = clampi(base[1] + ((counter & 2) ? 1 : 0), v.Y - 1);
-        const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
-        gradient_at(v, gc, cx, cy, cz, ngrad[counter]);
-        nval[counter] = (double)v.at(cx, cy, cz);
+        for (int oz = 0; oz < 2; ++oz)
+#pragma unroll
+          for (int oy = 0; oy < 2; ++oy) {
+            const T* __restrict__ r = p + oz * sxy + oy * sx;
+            const T n0 = __ldg(r), n1 = __ldg(r + 1);
+            ax[oz][oy][0] = (float)__ldg(r + xm); ax[oz][oy][1] = (float)n0;
+            ax[oz][oy][2] = (float)n1;            ax[oz][oy][3] = (float)__ldg(r + xp);
+            nval[oz * 4 + oy * 2] = (double)n0; nval[oz * 4 + oy * 2 + 1] = (double)n1;
+          }
+#pragma unroll
+        for (int oz = 0; oz < 2; ++oz)
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const T* __restrict__ r = p + oz * sxy + (j ? yp : ym);
+            ay[oz][j][0] = (float)__ldg(r); ay[oz][j][1] = (float)__ldg(r + 1);
+          }
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int oy = 0; oy < 2; ++oy) {
+            const T* __restrict__ r = p + oy * sx + (j ? zp : zm);
+            az[j][oy][0] = (float)__ldg(r); az[j][oy][1] = (float)__ldg(r + 1);
+          }
+#pragma unroll
+        for (int counter = 0; counter < 8; ++counter) {
+          const int ox = counter & 1, oy = (counter >> 1) & 1, oz = counter >> 2;
+          const float mid = is_fp<T>::value ? ax[oz][oy][ox + 1] : 0.0f;
+          const float xm = ax[oz][oy][ox], xp = ax[oz][oy][ox + 2];
+          const float ym = oy == 0 ? ay[oz][0][ox] : ax[oz][0][ox + 1], yp = oy == 0 ? ax[oz][1][ox + 1] : ay[oz][1][ox];
+          const float zm = oz == 0 ? az[0][oy][ox] : ax[0][oy][ox + 1], zp = oz == 0 ? ax[1][oy][ox + 1] : az[1][oy][ox];
+          { float s = 0.0f; s += (-gc[0]) * xm; s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
+          { float s = 0.0f; s += (-gc[1]) * ym; s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
+          { float s = 0.0f; s += (-gc[2]) * zm; s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
+        }
+      } else {
+#pragma unroll 1
+        for (int counter = 0; counter < 8; ++counter) {
+          const int cx = clampi(base[0] + ((counter & 1) ? 1 : 0), v.X - 1);
+          const int cy = clampi(base[1] + ((counter & 2) ? 1 : 0), v.Y - 1);
+          const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
+          float gtmp[3];
+          gradient_at(v, gc, cx, cy, cz, gtmp);
+          const double nv = (double)v.at(cx, cy, cz);
+          // (dynamic index into the register cache: written through a switch so that it stays in registers)
+#pragma unroll
+          for (int q = 0; q < 8; ++q)
+            if (q == counter) { ngrad[q][0] = gtmp[0]; ngrad[q][1] = gtmp[1]; ngrad[q][2] = gtmp[2]; nval[q] = nv; }
+        }
       }
     }
     double gd[3] = {0.0, 0.0, 0.0};
