@@ -287,7 +287,7 @@ int launch_project(cub_handle h, float* pts, size_t n) {
   a.work = h->d_totals + 7;
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
-  const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)kNumSMs * tuning_knob("CUB_PROJ_CTAS_PER_SM", 4));
+  const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)kNumSMs * tuning_knob("CUB_PROJ_CTAS_PER_SM", 5));
   DISPATCH_PIXEL(h->dtype, (k_project<T><<<blocks, 128, 0, h->stream>>>(a)));
   h->launches++;
   CU_TRY(h, cudaGetLastError());

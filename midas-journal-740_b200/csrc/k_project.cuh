@@ -86,7 +86,7 @@ __device__ __forceinline__ int clampi(long long v, int hi) { return v < 0 ? 0 : 
 // its vertex immediately takes the next one from a global counter instead of idling until the slowest vertex of
 // its warp is done.  The arithmetic per vertex is unchanged (and so are the results, bit for bit).
 template <typename T>
-__global__ void __launch_bounds__(128) k_project(const ProjArgs a) {
+__global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   VolView<T> v{static_cast<const T*>(a.vol), a.g.X, a.g.Y, a.g.Zl, a.g.zg0, a.g.Zg};
   float gc[3];
   double inv_sp[3];
