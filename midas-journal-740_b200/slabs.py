@@ -56,26 +56,62 @@ def all_gather_counts(n_points: int, n_cells: int, device=None) -> list[tuple[in
 
 
 def run_streamed(handles, vol_ptr: int, dtype, dims_xyz, params, n_slabs: int, out_points_ptr: int, out_cells_ptr: int,
-                 id_bytes: int = 4, halo: int = 2, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)):
+                 id_bytes: int = 4, halo: int = 2, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0),
+                 device_volume=None, streams=None):
     """One GPU, host volume in, host mesh out, streamed: the image is cut into `n_slabs` z-slabs that travel
     through `handles` (>= 2 capi.Handle objects, each on its own stream) round-robin, so the host->device copy
     of slab c+1, the kernels of slab c and the device->host copy of slab c-1 overlap.  Ids are global: the id
     base of a slab is the running sum of the counts of the slabs before it (the same exclusive scan the
     multi-GPU path gets from its all-gather).  `vol_ptr` / `out_*_ptr`: pinned host memory; the outputs must
-    be large enough for the whole mesh.  Returns (n_points, n_cells)."""
+    be large enough for the whole mesh.  Returns (n_points, n_cells).
+
+    Two ways for the volume to travel:
+    * default: every handle copies its slab *with* its halo slices into its own buffer (cub_set_volume with
+      CUB_MEM_HOST); works for volumes larger than the device memory, re-sends 2 * halo slices per cut;
+    * `device_volume` (a torch uint8 CUDA tensor of the volume's size) + `streams` (the torch streams the
+      handles were created on): the volume is copied once, in n_slabs consecutive pieces on a copy stream, into
+      that buffer and the handles borrow windows of it (CUB_MEM_DEVICE); nothing is sent twice."""
     import numpy as np
     from . import capi
     nx, ny, nz = dims_xyz
     item = np.dtype(dtype).itemsize
+    slice_bytes = ny * nx * item
     slabs = plan_slabs(nz, n_slabs, halo)
     verts_per_cell = 3 if params.generate_triangles else 4
     cells_per_quad = 2 if params.generate_triangles else 1
     pbase = cbase = 0
+    resident = device_volume is not None
+    events = []
+    if resident:
+        import ctypes
+        import torch
+        assert streams is not None and len(streams) == len(handles), "resident mode needs the handles' torch streams"
+        assert device_volume.is_cuda and device_volume.numel() * device_volume.element_size() >= nz * slice_bytes
+        dev = device_volume.view(torch.uint8).reshape(-1)
+        host = torch.from_numpy(np.ctypeslib.as_array((ctypes.c_uint8 * (nz * slice_bytes)).from_address(vol_ptr)))
+        copy_stream = _copy_stream(dev.device)
+        for st in streams:
+            copy_stream.wait_stream(st)  # earlier work on the handles may still read the buffer
+        done = 0
+        with torch.cuda.stream(copy_stream):
+            for s in slabs:  # piece c ends where slab c's window ends: after it, slab c has all it reads
+                a, b = done * slice_bytes, s.local_z1 * slice_bytes
+                if b > a:
+                    dev[a:b].copy_(host[a:b], non_blocking=True)
+                done = max(done, s.local_z1)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                events.append(ev)
 
     def upload(c):
         s, h = slabs[c], handles[c % len(handles)]
-        h.set_volume_ptr(vol_ptr + s.local_z0 * ny * nx * item, dtype, (nx, ny, s.local_z1 - s.local_z0), capi.MEM_HOST,
-                         spacing, origin)
+        if resident:
+            streams[c % len(handles)].wait_event(events[c])
+            h.set_volume_ptr(device_volume.data_ptr() + s.local_z0 * slice_bytes, dtype, (nx, ny, s.local_z1 - s.local_z0),
+                             capi.MEM_DEVICE, spacing, origin)
+        else:
+            h.set_volume_ptr(vol_ptr + s.local_z0 * slice_bytes, dtype, (nx, ny, s.local_z1 - s.local_z0), capi.MEM_HOST,
+                             spacing, origin)
         h.set_slab(nz, s.local_z0, s.own_z0, s.own_z1)
 
     upload(0)
@@ -93,3 +129,14 @@ def run_streamed(handles, vol_ptr: int, dtype, dims_xyz, params, n_slabs: int, o
     for h in handles:
         h.synchronize()
     return pbase, cbase
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    import torch
+    key = (device.type, device.index)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]

@@ -290,8 +290,9 @@ def test_raster_vertex_order_z_slabs(tri, proj):
     assert_mesh_equal_up_to_vertex_order(run(proj), ref, run(False), ref0, "raster slabs")
 
 
+@pytest.mark.parametrize("resident", [False, True])
 @pytest.mark.parametrize("n_slabs,n_handles", [(4, 2), (7, 3)])
-def test_streamed_slabs_from_host_memory(n_slabs, n_handles):
+def test_streamed_slabs_from_host_memory(n_slabs, n_handles, resident):
     """slabs.run_streamed: host volume in, host mesh out through several handles; equals the single run"""
     import torch
     P, O = pkg(), oracle()
@@ -302,9 +303,15 @@ def test_streamed_slabs_from_host_memory(n_slabs, n_handles):
     cells = torch.zeros((ref.cells.shape[0] + 8, 3), dtype=torch.int32).pin_memory()
     p = P.capi.default_params()
     p.iso_value, p.generate_triangles, p.project_vertices, p.surface_distance_threshold = 0.0, 1, 1, 0.01
-    handles = [P.capi.Handle(0) for _ in range(n_handles)]
+    kw = {}
+    if resident:  # the volume is copied once into a device buffer, the handles borrow windows of it
+        streams = [torch.cuda.Stream() for _ in range(n_handles)]
+        handles = [P.capi.Handle(0, st.cuda_stream) for st in streams]
+        kw = dict(device_volume=torch.empty(vol.nbytes, dtype=torch.uint8, device="cuda"), streams=streams)
+    else:
+        handles = [P.capi.Handle(0) for _ in range(n_handles)]
     n_pts, n_cells = P.slabs.run_streamed(handles, vt.data_ptr(), np.float32, (40, 28, 45), p, n_slabs, pts.data_ptr(),
-                                          cells.data_ptr(), halo=9)
+                                          cells.data_ptr(), halo=9, **kw)
     assert (n_pts, n_cells) == (ref.points.shape[0], ref.cells.shape[0])
     mesh = P.Mesh(pts.numpy()[:n_pts], cells.numpy()[:n_cells].view(np.uint32))
     assert_mesh_equal(mesh, ref, "streamed")
