@@ -66,6 +66,28 @@ def test_noise_volumes_ids_and_connectivity(dtype, shape, fill):
         assert_mesh_equal(mesh, ref, f"{dtype.__name__} {shape} tri={tri}")
 
 
+@pytest.mark.parametrize("shape", [(3, 2, 40000), (2, 30000, 5), (3000, 6, 7), (2, 2, 65534)])
+def test_extreme_aspect_ratios(shape):
+    """long rows / many rows / many slices: the 16 + 15 bit corner records, the per-slice id index, 32-bit indices"""
+    O = oracle()
+    vol, iso = random_volume(shape, np.uint8, seed=shape[0] + shape[1], fill=0.5)
+    for tri, order in ((False, 0), (True, 0)):
+        ref = O.cuberille(vol, iso, triangles=tri, project=False, mode=O.CLOSED_FORM)
+        assert_mesh_equal(run_filter(vol, iso, triangles=tri, project=False), ref, f"{shape} tri={tri}")
+
+
+def test_sizes_beyond_the_corner_record_are_refused():
+    P = pkg()
+    h = P.capi.Handle(0)
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = 1.0, 0, 0
+    for shape in [(1, 1, 65535), (1, 32767, 1)]:
+        h.set_volume(np.zeros(shape, np.uint8))
+        with pytest.raises(RuntimeError, match="not supported"):
+            h.count(p)
+    h.close()
+
+
 def test_noise_volume_literal_lookup_agrees_too():
     O = oracle()
     vol, iso = random_volume((14, 21, 45), np.uint8, seed=3)
