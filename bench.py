@@ -234,10 +234,14 @@ def main():
 
     last_counts = [None]
 
+    side_stream = torch.cuda.Stream() if N > 1 else None
+
     def step(params=prm, handle=None):
         hh = handle or h
         n_pts, n_quads = hh.count(params)
-        counts = P.slabs.all_gather_counts(n_pts, n_quads, dev)   # the only exchange of the data path
+        if N > 1:
+            hh.emit_vertices()   # needs no id base: runs while the counts are exchanged on a side stream
+        counts = P.slabs.all_gather_counts(n_pts, n_quads, dev, side_stream)   # the only exchange of the data path
         last_counts[0] = counts
         cells_per_quad = 2 if params.generate_triangles else 1
         pbase, cbase = P.slabs.exclusive_bases(counts, rank)

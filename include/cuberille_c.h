@@ -131,6 +131,14 @@ int cub_count(cub_handle h, const cub_params *p, uint64_t *n_points, uint64_t *n
  * (n_points, n_cells) returned by cub_count.  Default 0, 0.                    */
 int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base);
 
+/* Optional early half of cub_emit: queues the vertex stage (vertex creation
+ * order + AddVertex positions, txx:179-194, 257-276) of the current count on
+ * the handle's stream.  It needs the counts but not the id base, so a rank of a
+ * multi-GPU run calls it right after cub_count and exchanges its counts with
+ * the other ranks while it runs; cub_emit then skips the stage.  No effect if
+ * already done (or while cub_enable_timing is on).                            */
+int cub_emit_vertices(cub_handle h);
+
 /* Phase 2 of GenerateData: AddVertex (txx:257-276), ProjectVertexToIsoSurface
  * (txx:440-474) with ComputeGradientImage (txx:479-498) evaluated on the fly,
  * AddQuadFace (txx:279-332).  Results stay in device buffers owned by the

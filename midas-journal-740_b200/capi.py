@@ -26,7 +26,7 @@ CODE_DTYPES = {v: k for k, v in DTYPE_CODES.items()}
 # every symbol include/cuberille_c.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "cub_abi_version", "cub_default_params", "cub_create", "cub_destroy", "cub_last_error", "cub_set_volume",
-    "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
+    "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit_vertices", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
     "cub_synchronize", "cub_device_buffers",
     "cub_debug_bitmask", "cub_debug_project_points", "cub_generate_volume", "cub_download_volume",
     "cub_enable_timing", "cub_get_timings", "cub_launch_count",
@@ -89,6 +89,8 @@ def load() -> C.CDLL:
     L.cub_set_id_base.restype = i
     L.cub_set_id_base.argtypes = [vp, u64, u64]
     L.cub_emit.restype = i
+    L.cub_emit_vertices.restype = i
+    L.cub_emit_vertices.argtypes = [vp]
     L.cub_emit.argtypes = [vp, i]
     L.cub_run.restype = i
     L.cub_run.argtypes = [vp, C.POINTER(Params), i, pu64, pu64]
@@ -198,6 +200,10 @@ class Handle:
 
     def set_id_base(self, point_base: int, cell_base: int):
         self._check(self._L.cub_set_id_base(self._h, point_base, cell_base))
+
+    def emit_vertices(self):
+        """Queue the vertex stage now (before the id base is known); emit() then only emits the cells."""
+        self._check(self._L.cub_emit_vertices(self._h))
 
     def emit(self, id_bytes: int = 4):
         self._check(self._L.cub_emit(self._h, id_bytes))

@@ -118,6 +118,7 @@ struct cub_handle_s {
   Grid g{};
   bool counted = false, emitted = false;
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
+  bool vertices_done = false;   // the vertex stage of the current count has been queued (cub_emit_vertices)
   uint64_t n_points = 0, n_quads = 0, n_cells = 0, ghost_v = 0, ghost_f = 0;
   uint64_t point_base = 0, cell_base = 0;
   int id_bytes = 4, verts_per_cell = 4;
@@ -598,6 +599,7 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   h->n_quads = tot_f - h->ghost_f;
   h->point_base = h->cell_base = 0;
   h->counted = true;
+  h->vertices_done = false;
   if (n_points) *n_points = h->n_points;
   if (n_quads) *n_quads = h->n_quads;
   return CUB_OK;
@@ -608,6 +610,75 @@ int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base)
   h->point_base = point_id_base;
   h->cell_base = cell_id_base;
   return CUB_OK;
+}
+
+// The vertex stage of cub_emit: K3a + K3b (reference order) or k_points_raster.  It needs the counts but not the
+// id base, so a multi-GPU caller can queue it before the ranks have exchanged their counts (cub_emit_vertices).
+static int emit_vertex_stage(cub_handle h) {
+  const cub_params& P = h->params;
+  const Grid& g = h->g;
+  const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0;
+  const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
+  const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
+  CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
+  if (!h->raster) {
+    CUB_TRY(ensure(h, h->vtx, n_pts_all));
+    CUB_TRY(ensure(h, h->vsl, (size_t)(h->zs1 - h->owner_z_min) + 1 + (n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds));
+    CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
+  }
+  h->vertices_done = true;
+  if (h->n_quads == 0) return CUB_OK;
+  const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
+  if (!h->raster) {
+    {
+      // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
+      SweepArgs a{};
+      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
+      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
+      a.vofs = h->vofs.p; a.vtx = h->vtx.p;
+      CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
+      h->launches++;
+    }
+    {
+      // K3b: points + corner -> id map
+      const int nz = h->zs1 - h->owner_z_min;
+      const unsigned n_blocks = (unsigned)((n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds);
+      SliceIndexArgs si{};
+      si.vofs = h->vofs.p; si.plane_entries = (size_t)h->EY * h->EW; si.z_first = h->owner_z_min; si.nz = nz;
+      si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
+      const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
+      k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
+      h->launches++;
+      VertexArgs a{};
+      a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
+      a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
+      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
+      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
+      a.points = h->points.p; a.perm = h->perm.p;
+      k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
+  } else {
+    // raster order: vertex id = corner slot, points straight from the active masks
+    RasterPointArgs a{};
+    a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
+    a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
+    a.zg0 = g.zg0; a.geom = h->geom; a.points = h->points.p;
+    const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
+    k_points_raster<<<grid, 256, 0, h->stream>>>(a);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
+  return CUB_OK;
+}
+
+int cub_emit_vertices(cub_handle h) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_emit_vertices before cub_count");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (h->vertices_done || h->timing) return CUB_OK;  // (per-kernel timing keeps the whole emission inside cub_emit)
+  return emit_vertex_stage(h);
 }
 
 int cub_emit(cub_handle h, int id_bytes) {
@@ -626,13 +697,7 @@ int cub_emit(cub_handle h, int id_bytes) {
     return fail(h, CUB_ERR_OVERFLOW, "point ids up to %llu do not fit 32 bits", (unsigned long long)(h->point_base + h->n_points));
 
   const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
-  CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
   CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
-  if (!h->raster) {
-    CUB_TRY(ensure(h, h->vtx, n_pts_all));
-    CUB_TRY(ensure(h, h->vsl, (size_t)(h->zs1 - h->owner_z_min) + 1 + (n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds));
-    CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
-  }
   if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
   if (cd) CUB_TRY(ensure(h, h->celldata, (size_t)h->n_cells * h->pix_bytes));
 
@@ -641,47 +706,7 @@ int cub_emit(cub_handle h, int id_bytes) {
   const unsigned long long id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
   if (h->n_quads > 0) {
     Timer t(h, 2);
-    if (!h->raster) {
-      {
-        // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
-        SweepArgs a{};
-        a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
-        a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-        a.vofs = h->vofs.p; a.vtx = h->vtx.p;
-        CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
-        h->launches++;
-      }
-      {
-        // K3b: points + corner -> id map
-        const int nz = h->zs1 - h->owner_z_min;
-        const unsigned n_blocks = (unsigned)((n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds);
-        SliceIndexArgs si{};
-        si.vofs = h->vofs.p; si.plane_entries = (size_t)h->EY * h->EW; si.z_first = h->owner_z_min; si.nz = nz;
-        si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
-        const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
-        k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
-        h->launches++;
-        VertexArgs a{};
-        a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
-        a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
-        a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
-        a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
-        a.points = h->points.p; a.perm = h->perm.p;
-        k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
-        h->launches++;
-        CU_TRY(h, cudaGetLastError());
-      }
-    } else {
-      // raster order: vertex id = corner slot, points straight from the active masks
-      RasterPointArgs a{};
-      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
-      a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
-      a.zg0 = g.zg0; a.geom = h->geom; a.points = h->points.p;
-      const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
-      k_points_raster<<<grid, 256, 0, h->stream>>>(a);
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
-    }
+    if (!h->vertices_done) CUB_TRY(emit_vertex_stage(h));
     {
       // K3c: faces
       FaceArgs a{};

@@ -40,18 +40,23 @@ def exclusive_bases(counts: list[tuple[int, int]], rank: int) -> tuple[int, int]
     return sum(c[0] for c in counts[:rank]), sum(c[1] for c in counts[:rank])
 
 
-def all_gather_counts(n_points: int, n_cells: int, device=None) -> list[tuple[int, int]]:
+def all_gather_counts(n_points: int, n_cells: int, device=None, stream=None) -> list[tuple[int, int]]:
     """All-gather of the per-rank (points, cells) counts: NCCL has no exclusive scan, so every rank gathers
-    the 2 x world integers and sums its prefix locally.  Single process: no communication."""
+    the 2 x world integers and sums its prefix locally.  Single process: no communication.
+    `stream`: a side torch stream for the exchange, so that it does not queue behind kernels the caller has
+    already launched on the current stream (Handle.emit_vertices runs meanwhile)."""
+    import contextlib
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
         return [(int(n_points), int(n_cells))]
     world = dist.get_world_size()
-    mine = torch.tensor([n_points, n_cells], dtype=torch.int64, device=device)
-    out = torch.empty(2 * world, dtype=torch.int64, device=device)
-    dist.all_gather_into_tensor(out, mine)
-    flat = out.cpu().tolist()
+    ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+    with ctx:
+        mine = torch.tensor([n_points, n_cells], dtype=torch.int64, device=device)
+        out = torch.empty(2 * world, dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(out, mine)
+        flat = out.cpu().tolist()
     return [(flat[2 * r], flat[2 * r + 1]) for r in range(world)]
 
 
