@@ -23,6 +23,7 @@
 #include "k_faces.cuh"
 #include "k_project.cuh"
 #include "k_sweep.cuh"
+#include "k_assign.cuh"
 #include "k_vertices.cuh"
 
 using namespace cub;
@@ -96,6 +97,7 @@ struct cub_handle_s {
 
   // scratch
   DevBuf<uint32_t> bits, cnt, act, vofs, fofs, cofs, perm;
+  DevBuf<uint4> own;         // K2a -> K3a: the 8 ownership masks per voxel word (2 x uint4 per entry)
   DevBuf<uint32_t> vtx;
   DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
   uint64_t ent_layout[3] = {0, 0, 0};
@@ -118,6 +120,7 @@ struct cub_handle_s {
   Grid g{};
   bool counted = false, emitted = false;
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
+  bool own_valid = false;       // K2a stored the ownership masks of the current count
   bool vertices_done = false;   // the vertex stage of the current count has been queued (cub_emit_vertices)
   uint64_t n_points = 0, n_quads = 0, n_cells = 0, ghost_v = 0, ghost_f = 0;
   uint64_t point_base = 0, cell_base = 0;
@@ -372,7 +375,7 @@ int cub_destroy(cub_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
-  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->vsl.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
+  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->own.p); cudaFree(h->vsl.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
   cudaFree(h->d_ticket); cudaFree(h->d_totals);
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
@@ -494,6 +497,8 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   CUB_TRY(ensure(h, h->vofs, entries));
   CUB_TRY(ensure(h, h->fofs, entries));
   CUB_TRY(ensure(h, h->cofs, entries + 4));
+  const bool keep_own = p->vertex_order != CUB_ORDER_RASTER && tuning_knob("CUB_ASSIGN_SWEEP", 0) == 0;
+  if (keep_own) CUB_TRY(ensure(h, h->own, 2 * entries));
   // entries that K2a never writes (padding columns) must read as zero counts
   if (!had_e || layout_changed) CU_TRY(h, cudaMemsetAsync(h->cnt.p, 0, entries * 4, h->stream));
 
@@ -512,7 +517,8 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   CUB_TRY(ensure(h, h->status, 3 * n_tiles));
   SweepArgs ca{};
   ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
-  ca.cnt = h->cnt.p; ca.act = h->act.p;
+  ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = keep_own ? h->own.p : nullptr;
+  h->own_valid = keep_own;
   const int n_chunks = h->timing ? 1 : std::max(1, std::min(std::min(tuning_knob("CUB_CHUNKS", 1), 16), (h->zs1 - h->owner_z_min) / 64));
   if (n_chunks == 1) {
     // serial: K1 then K2a on the handle's stream (also the per-kernel timing path)
@@ -630,8 +636,18 @@ static int emit_vertex_stage(cub_handle h) {
   if (h->n_quads == 0) return CUB_OK;
   const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
   if (!h->raster) {
-    {
-      // K3a: vertex id -> lattice corner (z-sweep over the scan range, reference creation order)
+    if (h->own_valid) {
+      // K3a: vertex id -> lattice corner, walking the ownership masks K2a stored (reference creation order)
+      AssignArgs a{};
+      a.cnt = h->cnt.p; a.vofs = h->vofs.p; a.own = h->own.p;
+      a.X = g.X; a.Y = g.Y; a.Wx = g.Wx; a.EY = h->EY; a.EW = h->EW; a.z_begin = h->owner_z_min;
+      a.vtx = h->vtx.p;
+      const dim3 grid((g.Wx + 31) / 32, (g.Y + 7) / 8, h->zs1 - h->owner_z_min);
+      k_assign<<<grid, 256, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    } else {
+      // K3a, first version: a second z-sweep that recomputes the ownership masks (CUB_ASSIGN_SWEEP=1)
       SweepArgs a{};
       a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
       a.z_begin = h->owner_z_min; a.z_end = h->zs1;

@@ -44,6 +44,8 @@ struct SweepArgs {
   // --- count
   uint32_t* cnt;       // [Zl+1][EY][EW] packed owned corners | faces << 10 | active corners << 20
   uint32_t* act;       // [Zl+1][EY][EW] active-corner mask of the corner word
+  uint4* own;          // [Zl+1][EY][EW][2] the 8 ownership masks of the voxel word, written where it owns a corner
+                       // (may be null: raster vertex order does not need them)
   // --- assign
   const uint32_t* vofs;      // [Zl+1][EY][EW] exclusive scan of the owned-corner counts
   uint32_t* vtx;             // [n vertices] cx | cy << 16 | oz << 31  (oz: the corner is on the owner slice's upper plane;
@@ -292,6 +294,11 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
 #pragma unroll
             for (int l = 0; l < 8; ++l) nv += __popc(O[l]);
             packed = nv | (nf << 10);
+            if (nv && a.own) {  // k_assign walks these instead of sweeping again
+              uint4* __restrict__ o = a.own + 2 * ((size_t)z * plane_entries + (size_t)(e0 + k * a.EW));
+              __stcs(o, make_uint4(O[0], O[1], O[2], O[3]));
+              __stcs(o + 1, make_uint4(O[4], O[5], O[6], O[7]));
+            }
           }
           if (cor) {
             packed |= (uint32_t)__popc(act_prev[k]) << 20;
