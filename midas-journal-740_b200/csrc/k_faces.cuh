@@ -55,15 +55,26 @@ __device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, uin
   }
 }
 
+// Cell data = the pixel of the generating voxel (both triangles of a quad get it).  The pixel is loaded once per
+// voxel as raw bytes (1, 2, 4 or 8) and stored with one typed store per cell.
+__device__ __forceinline__ unsigned long long load_pixel(const void* vol, size_t voxel, int pix_bytes) {
+  switch (pix_bytes) {
+    case 1: return __ldg(reinterpret_cast<const uint8_t*>(vol) + voxel);
+    case 2: return __ldg(reinterpret_cast<const uint16_t*>(vol) + voxel);
+    case 4: return __ldg(reinterpret_cast<const uint32_t*>(vol) + voxel);
+    default: return __ldg(reinterpret_cast<const unsigned long long*>(vol) + voxel);
+  }
+}
+
 template <int MODE>
-__device__ __forceinline__ void write_celldata(const FaceArgs& a, size_t fidx, size_t voxel) {
-  const unsigned char* src = reinterpret_cast<const unsigned char*>(a.vol) + voxel * a.pix_bytes;
+__device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx, unsigned long long pix) {
   const bool two = (MODE != kEmitQuads);
-  unsigned char* dst = reinterpret_cast<unsigned char*>(a.celldata) + (two ? 2 * fidx : fidx) * a.pix_bytes;
-  for (int bb = 0; bb < a.pix_bytes; ++bb) {
-    const unsigned char v = src[bb];
-    dst[bb] = v;
-    if (two) dst[a.pix_bytes + bb] = v;
+  const size_t c = two ? 2 * (size_t)fidx : (size_t)fidx;
+  switch (a.pix_bytes) {
+    case 1: { uint8_t* d = reinterpret_cast<uint8_t*>(a.celldata) + c; d[0] = (uint8_t)pix; if (two) d[1] = (uint8_t)pix; break; }
+    case 2: { uint16_t* d = reinterpret_cast<uint16_t*>(a.celldata) + c; d[0] = (uint16_t)pix; if (two) d[1] = (uint16_t)pix; break; }
+    case 4: { uint32_t* d = reinterpret_cast<uint32_t*>(a.celldata) + c; d[0] = (uint32_t)pix; if (two) d[1] = (uint32_t)pix; break; }
+    default: { unsigned long long* d = reinterpret_cast<unsigned long long*>(a.celldata) + c; d[0] = pix; if (two) d[1] = pix; break; }
   }
 }
 
@@ -203,7 +214,8 @@ __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
         if (need[l]) vid[l] = __ldg(a.perm + vid[l]);
     }
     // the voxel behind the face (cell data): word src of this warp's row
-    const size_t voxel = a.celldata ? ((size_t)zl * g.Y + y) * g.X + (size_t)(blockIdx.x * 32 + src) * 32 + b : 0;
+    const unsigned long long voxel =
+        a.celldata ? load_pixel(a.vol, ((size_t)zl * g.Y + y) * g.X + (size_t)(blockIdx.x * 32 + src) * 32 + b, a.pix_bytes) : 0ull;
     if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
