@@ -32,6 +32,22 @@ struct FaceArgs {
   int pix_bytes;
 };
 
+// two triangles = 6 ids: 24 bytes (8-byte aligned) as three 8-byte stores, or 48 bytes as three 16-byte stores
+template <typename IdT>
+__device__ __forceinline__ void store_tri_pair(IdT* c, IdT a0, IdT a1, IdT a2, IdT b0, IdT b1, IdT b2) {
+  if (sizeof(IdT) == 4) {
+    uint2* d = reinterpret_cast<uint2*>(c);
+    d[0] = make_uint2((uint32_t)a0, (uint32_t)a1);
+    d[1] = make_uint2((uint32_t)a2, (uint32_t)b0);
+    d[2] = make_uint2((uint32_t)b1, (uint32_t)b2);
+  } else {
+    ulonglong2* d = reinterpret_cast<ulonglong2*>(c);
+    d[0] = make_ulonglong2((unsigned long long)a0, (unsigned long long)a1);
+    d[1] = make_ulonglong2((unsigned long long)a2, (unsigned long long)b0);
+    d[2] = make_ulonglong2((unsigned long long)b1, (unsigned long long)b2);
+  }
+}
+
 template <typename IdT, int MODE>
 __device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
   if (MODE == kEmitScratchQuads) {
@@ -44,14 +60,14 @@ __device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, uin
     c += (size_t)fidx * 4;
     if (sizeof(IdT) == 4) {
       *reinterpret_cast<uint4*>(c) = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, (uint32_t)v3);
-    } else {
-      c[0] = v0; c[1] = v1; c[2] = v2; c[3] = v3;
+    } else {  // 32-byte cells: two 16-byte stores
+      reinterpret_cast<ulonglong2*>(c)[0] = make_ulonglong2((unsigned long long)v0, (unsigned long long)v1);
+      reinterpret_cast<ulonglong2*>(c)[1] = make_ulonglong2((unsigned long long)v2, (unsigned long long)v3);
     }
   } else {
     // unprojected quad: both diagonals are equal, `>=` takes the first split (txx:298-302)
     c += (size_t)fidx * 6;
-    c[0] = v0; c[1] = v1; c[2] = v3;
-    c[3] = v1; c[4] = v2; c[5] = v3;
+    store_tri_pair<IdT>(c, v0, v1, v3, v1, v2, v3);
   }
 }
 
@@ -253,13 +269,8 @@ __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ q
 #pragma unroll
   for (int k = 0; k < 4; ++k) v[k] = (IdT)((unsigned long long)id[k] + id_delta);
   IdT* c = tris + i * 6;
-  if (d02 >= d13) {
-    c[0] = v[0]; c[1] = v[1]; c[2] = v[3];
-    c[3] = v[1]; c[4] = v[2]; c[5] = v[3];
-  } else {
-    c[0] = v[0]; c[1] = v[1]; c[2] = v[2];
-    c[3] = v[0]; c[4] = v[2]; c[5] = v[3];
-  }
+  const bool first = d02 >= d13;  // (0,1,3),(1,2,3) else (0,1,2),(0,2,3)
+  store_tri_pair<IdT>(c, v[0], v[1], first ? v[3] : v[2], first ? v[1] : v[0], v[2], v[3]);
 }
 
 }  // namespace cub
