@@ -129,9 +129,6 @@ struct cub_handle_s {
 
   bool timing = false;
   cudaEvent_t ev[10] = {};
-  cudaStream_t aux = nullptr;          // second stream: issue-bound sweeps run beside the HBM-bound classify
-  cudaEvent_t chunk_ev[16] = {};       // per z-chunk "classified" events
-  cudaEvent_t fork_ev = nullptr, join_ev = nullptr;
   float ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   uint64_t launches = 0;
 };
@@ -360,10 +357,6 @@ int cub_create(int device, void* stream, cub_handle* out) {
             cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)) == cudaSuccess &&
             cudaMallocHost(&h->h_totals, 8 * sizeof(unsigned long long)) == cudaSuccess;
   for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
-  ok = ok && cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess;
-  for (int i = 0; ok && i < 16; ++i) ok = cudaEventCreateWithFlags(&h->chunk_ev[i], cudaEventDisableTiming) == cudaSuccess;
-  ok = ok && cudaEventCreateWithFlags(&h->fork_ev, cudaEventDisableTiming) == cudaSuccess &&
-       cudaEventCreateWithFlags(&h->join_ev, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
   cub_default_params(&h->params);
   *out = h;
@@ -380,10 +373,6 @@ int cub_destroy(cub_handle h) {
   if (h->h_totals) cudaFreeHost(h->h_totals);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
   for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
-  for (int i = 0; i < 16; ++i) if (h->chunk_ev[i]) cudaEventDestroy(h->chunk_ev[i]);
-  if (h->fork_ev) cudaEventDestroy(h->fork_ev);
-  if (h->join_ev) cudaEventDestroy(h->join_ev);
-  if (h->aux) cudaStreamDestroy(h->aux);
   if (h->own_stream) cudaStreamDestroy(h->stream);
   delete h;
   return CUB_OK;
@@ -519,9 +508,9 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
   ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = keep_own ? h->own.p : nullptr;
   h->own_valid = keep_own;
-  const int n_chunks = h->timing ? 1 : std::max(1, std::min(std::min(tuning_knob("CUB_CHUNKS", 1), 16), (h->zs1 - h->owner_z_min) / 64));
-  if (n_chunks == 1) {
-    // serial: K1 then K2a on the handle's stream (also the per-kernel timing path)
+  {
+    // K1 then K2a on the handle's stream.  (Running the HBM-bound K1 beside the issue-bound K2a, on two streams by
+    // z-chunks or even without any dependency, was measured in r1 and took K1 + K2a: DESIGN.md section 8.)
     {
       Timer t(h, 0);
       DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, 0, g.Zl, h->stream, 32));
@@ -532,31 +521,6 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
     ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
     CU_TRY(h, dispatch_sweep<MODE_COUNT>(ca, h->stream));
     h->launches++;
-  } else {
-    // (opt-in, CUB_CHUNKS > 1; r1 measurement: no gain yet - the sweep's 80 registers leave room for one of its
-    //  CTAs next to the classify CTAs)
-    // z-chunk pipeline: the HBM-bound classify of chunk c+1 (handle's stream, a few CTAs per SM) runs beside
-    // the issue-bound count sweep of chunk c (aux stream).  The sweep of chunk [a, b) reads slices a-1 .. b,
-    // so classify chunk c covers the slices up to and including cut(c+1).
-    const int z_lo = h->owner_z_min, z_hi = h->zs1;
-    auto cut = [&](int c) { return z_lo + (int)((long long)(z_hi - z_lo) * c / n_chunks); };
-    CU_TRY(h, cudaEventRecord(h->fork_ev, h->stream));
-    CU_TRY(h, cudaStreamWaitEvent(h->aux, h->fork_ev, 0));
-    for (int c = 0; c < n_chunks; ++c) {
-      const int a0 = (c == 0) ? 0 : cut(c) + 1;
-      const int a1 = (c == n_chunks - 1) ? g.Zl : std::min(cut(c + 1) + 1, g.Zl);
-      if (a1 > a0) {
-        DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, a0, a1, h->stream, tuning_knob("CUB_K1_CTAS", 4)));
-        CU_TRY(h, cudaGetLastError());
-      }
-      CU_TRY(h, cudaEventRecord(h->chunk_ev[c], h->stream));
-      CU_TRY(h, cudaStreamWaitEvent(h->aux, h->chunk_ev[c], 0));
-      ca.z_begin = cut(c); ca.z_end = cut(c + 1);
-      CU_TRY(h, dispatch_sweep<MODE_COUNT>(ca, h->aux));
-      h->launches++;
-    }
-    CU_TRY(h, cudaEventRecord(h->join_ev, h->aux));
-    CU_TRY(h, cudaStreamWaitEvent(h->stream, h->join_ev, 0));
   }
   {
     CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
