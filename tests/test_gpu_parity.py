@@ -156,6 +156,18 @@ def test_save_pixel_as_cell_data(tri, proj):
     assert mesh.cell_data.dtype == np.int16 and (mesh.cell_data >= iso).all()
 
 
+@pytest.mark.parametrize("dtype", [np.uint8, np.uint16, np.float32, np.float64])
+def test_cell_data_pixel_widths(dtype):
+    """1-, 2-, 4- and 8-byte pixels through the typed cell-data stores (quads and fixed-split triangles)"""
+    O = oracle()
+    vol, iso = random_volume((9, 11, 70), dtype, seed=21, fill=0.45)
+    for tri in (False, True):
+        ref = O.cuberille(vol, iso, triangles=tri, project=False, cell_data=True, mode=O.CLOSED_FORM)
+        mesh = run_filter(vol, iso, triangles=tri, project=False, cell_data=True)
+        assert_mesh_equal(mesh, ref, f"celldata {np.dtype(dtype).name} tri={tri}")
+        assert mesh.cell_data.dtype == np.dtype(dtype)
+
+
 def test_64_bit_ids():
     O = oracle()
     vol, iso = random_volume((10, 12, 40), np.uint8, seed=9)
