@@ -74,7 +74,12 @@ typedef struct cub_params {
                                    (txx:82-85)                                  */
   double   step_relaxation;     /* h:222-223, default 0.95                      */
   uint32_t max_steps;           /* h:227-228, default 50                        */
-  uint32_t reserved1;
+  uint32_t image_border_faces;  /* 0 (default): the reference's behaviour, a neighbour outside
+                                 * the image reads the clamped pixel, so the image border never
+                                 * gets a face (open mesh there, h:55-57).  1: a neighbour outside
+                                 * the image counts as outside the surface, i.e. the mesh of the
+                                 * image padded with one outside layer: always closed (the
+                                 * "handle voxels on the edge of the image" TODO, txx:133)       */
 } cub_params;
 
 /* Fills *p with the constructor defaults of txx:31-41

@@ -142,6 +142,13 @@ public:
   itkSetMacro( RasterVertexOrder, bool );
   itkBooleanMacro( RasterVertexOrder );
 
+  /** Opt-in, off by default (no counterpart in the reference, which leaves the mesh open where the
+   * surface meets the image border, h:55-57 / the TODO at txx:133): treat everything outside the image
+   * as outside the surface, i.e. mesh the image as if it were padded with one outside layer. */
+  itkGetMacro( ImageBorderFaces, bool );
+  itkSetMacro( ImageBorderFaces, bool );
+  itkBooleanMacro( ImageBorderFaces );
+
   /** Projection knobs with the reference's clamp ranges (h:209-228). */
   itkGetMacro( ProjectVertexSurfaceDistanceThreshold, double );
   itkSetClampMacro( ProjectVertexSurfaceDistanceThreshold, double, 0.0, NumericTraits<InputPixelType>::max() );
@@ -166,6 +173,7 @@ protected:
     m_ProjectVerticesToIsoSurface = true;
     m_SavePixelAsCellData = false;
     m_RasterVertexOrder = false;
+    m_ImageBorderFaces = false;
     m_ProjectVertexSurfaceDistanceThreshold = 0.5;
     m_ProjectVertexStepLength = -1.0;
     m_ProjectVertexStepLengthRelaxationFactor = 0.95;
@@ -243,6 +251,7 @@ protected:
     params.project_vertices = m_ProjectVerticesToIsoSurface ? 1 : 0;
     params.save_pixel_as_cell_data = m_SavePixelAsCellData ? 1 : 0;
     params.vertex_order = m_RasterVertexOrder ? CUB_ORDER_RASTER : CUB_ORDER_REFERENCE;
+    params.image_border_faces = m_ImageBorderFaces ? 1u : 0u;
     params.surface_distance_threshold = m_ProjectVertexSurfaceDistanceThreshold;
     params.step_length = m_ProjectVertexStepLength;
     params.step_relaxation = m_ProjectVertexStepLengthRelaxationFactor;
@@ -313,6 +322,7 @@ private:
   bool                m_ProjectVerticesToIsoSurface;
   bool                m_SavePixelAsCellData;
   bool                m_RasterVertexOrder;
+  bool                m_ImageBorderFaces;
   double              m_ProjectVertexSurfaceDistanceThreshold;
   double              m_ProjectVertexStepLength;
   double              m_ProjectVertexStepLengthRelaxationFactor;

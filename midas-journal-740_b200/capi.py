@@ -44,7 +44,7 @@ class Params(C.Structure):
         ("step_length", C.c_double),
         ("step_relaxation", C.c_double),
         ("max_steps", C.c_uint32),
-        ("reserved1", C.c_uint32),
+        ("image_border_faces", C.c_uint32),
     ]
 
 

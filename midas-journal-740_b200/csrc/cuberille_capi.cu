@@ -30,7 +30,8 @@ using namespace cub;
 
 namespace {
 
-constexpr int kNumSMs = 148;
+// SMs of the device the handles run on (148 on a B200; refreshed by cub_create): grid sizes are multiples of it
+int kNumSMs = 148;
 
 // slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
 int pick_tz(int gx, int gy, int nz) {
@@ -117,7 +118,9 @@ struct cub_handle_s {
 
   // state
   cub_params params{};
-  Grid g{};
+  Grid g{};    // the lattice every kernel after K1 works on: the buffer, or (image_border_faces) the buffer padded by one layer
+  Grid gv{};   // the voxel buffer itself (K1, K4, cell data)
+  int pad = 0, zpad_lo = 0;  // image_border_faces: lattice (x, y, z) is voxel (x - pad, y - pad, z - zpad_lo)
   bool counted = false, emitted = false;
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
   bool own_valid = false;       // K2a stored the ownership masks of the current count
@@ -253,18 +256,32 @@ struct ClassifyPacked<T, true> {
 
 template <typename T>
 void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas_per_sm) {
+  const unsigned long long max_blocks = (unsigned long long)kNumSMs * ctas_per_sm;
+  h->launches++;
+  if (h->pad) {
+    // the padded lattice (image_border_faces): z0 / z1 are lattice slices
+    const Grid& gb = h->g;
+    const Grid& gv = h->gv;
+    const unsigned long long words = (unsigned long long)gb.Wx * gb.Y * (z1 - z0);  // < 2^32: checked by cub_count
+    const unsigned long long blocks = std::max<unsigned long long>(1, std::min((words + 7) / 8, max_blocks));
+    uint32_t* bits = h->bits.p + (size_t)z0 * gb.Y * gb.Wp;
+    // slice z0 of the launch is lattice slice z0: the kernel's z origin moves with it
+    const T* vol = static_cast<const T*>(h->d_vol);
+    Grid sub = gb;
+    k_classify_padded<T><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, sub, gv.X, gv.Y, gv.Zl, h->zpad_lo - z0,
+                                                                (T)h->params.iso_value, (unsigned)words);
+    return;
+  }
   Grid g = h->g;
   const unsigned groups = (unsigned)((g.Wx + kWordsPerTask - 1) / kWordsPerTask);
   const unsigned long long rows = (unsigned long long)g.Y * (z1 - z0);
   const unsigned tasks = (unsigned)(rows * groups);  // dims < 2^31 and cub_count checks rows*groups < 2^32
   unsigned long long blocks = ((unsigned long long)tasks + 7) / 8;
-  const unsigned long long max_blocks = (unsigned long long)kNumSMs * ctas_per_sm;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
   const bool full = (g.X % 32 == 0) && (g.Wx % kWordsPerTask == 0);
   const T* vol = static_cast<const T*>(h->d_vol) + (size_t)z0 * g.Y * g.X;
   uint32_t* bits = h->bits.p + (size_t)z0 * g.Y * g.Wp;
-  h->launches++;
   if (ClassifyPacked<T>::launch(h, vol, bits, g, rows, max_blocks, stream)) return;
   if (full)
     k_classify<T, true><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
@@ -276,7 +293,7 @@ int launch_project(cub_handle h, float* pts, size_t n) {
   if (n == 0) return CUB_OK;
   ProjArgs a;
   a.vol = h->d_vol;
-  a.g = h->g;
+  a.g = h->gv;
   a.geom = h->geom;
   a.iso = iso_as_pixel(h->dtype, h->params.iso_value);
   a.thr = h->params.surface_distance_threshold;
@@ -298,16 +315,33 @@ int launch_project(cub_handle h, float* pts, size_t n) {
 // geometry of the run: Grid + own range in local coordinates
 int setup_grid(cub_handle h) {
   if (!h->has_volume) return fail(h, CUB_ERR_INVALID, "no volume set");
+  Grid& gv = h->gv;
+  gv.X = (int)h->dims[0];
+  gv.Y = (int)h->dims[1];
+  gv.Zl = (int)h->dims[2];
+  gv.Wx = (gv.X + 31) / 32;
+  gv.Wp = (gv.Wx + 3) & ~3;
+  gv.zg0 = (int)h->local_z0;
+  gv.Zg = (int)h->image_nz;
+  // image_border_faces: everything after K1 runs on the image padded with one outside layer (x and y always, z
+  // where the local buffer touches the end of the image), in the padded image's coordinates
+  const int pad = h->params.image_border_faces ? 1 : 0;
+  const int zlo = (pad && h->local_z0 == 0) ? 1 : 0;
+  const int zhi = (pad && h->local_z0 + h->dims[2] == h->image_nz) ? 1 : 0;
+  h->pad = pad;
+  h->zpad_lo = zlo;
   Grid& g = h->g;
-  g.X = (int)h->dims[0];
-  g.Y = (int)h->dims[1];
-  g.Zl = (int)h->dims[2];
+  g.X = gv.X + 2 * pad;
+  g.Y = gv.Y + 2 * pad;
+  g.Zl = gv.Zl + zlo + zhi;
   g.Wx = (g.X + 31) / 32;
   g.Wp = (g.Wx + 3) & ~3;
-  g.zg0 = (int)h->local_z0;
-  g.Zg = (int)h->image_nz;
-  h->zs0 = (int)(h->own_z0 - h->local_z0);
-  h->zs1 = (int)(h->own_z1 - h->local_z0);
+  g.zg0 = gv.zg0 + pad - zlo;
+  g.Zg = gv.Zg + 2 * pad;
+  const long long own0 = (pad && h->own_z0 == 0) ? 0 : (long long)h->own_z0 + pad;
+  const long long own1 = (pad && h->own_z1 == h->image_nz) ? (long long)h->image_nz + 2 : (long long)h->own_z1 + pad;
+  h->zs0 = (int)(own0 - g.zg0);
+  h->zs1 = (int)(own1 - g.zg0);
   h->owner_z_min = (h->own_z0 > 0) ? h->zs0 - 1 : h->zs0;
   return CUB_OK;
 }
@@ -352,6 +386,10 @@ int cub_create(int device, void* stream, cub_handle* out) {
   } else {
     if (cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) { delete h; return CUB_ERR_CUDA; }
     h->own_stream = true;
+  }
+  {
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) kNumSMs = sms;
   }
   bool ok = cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
             cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)) == cudaSuccess &&
@@ -633,7 +671,7 @@ static int emit_vertex_stage(cub_handle h) {
       a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
-      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0; a.geom = h->geom;
+      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0 - h->pad; a.cpad = h->pad; a.geom = h->geom;
       a.points = h->points.p; a.perm = h->perm.p;
       k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
       h->launches++;
@@ -644,7 +682,7 @@ static int emit_vertex_stage(cub_handle h) {
     RasterPointArgs a{};
     a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
     a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
-    a.zg0 = g.zg0; a.geom = h->geom; a.points = h->points.p;
+    a.zg0 = g.zg0 - h->pad; a.cpad = h->pad; a.geom = h->geom; a.points = h->points.p;
     const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
     k_points_raster<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
@@ -698,6 +736,7 @@ int cub_emit(cub_handle h, int id_bytes) {
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
       a.mode = mode;
       a.vol = cd ? h->d_vol : nullptr;
+      a.vX = h->gv.X; a.vY = h->gv.Y; a.vpad = h->pad; a.vzpad = h->zpad_lo;
       a.celldata = cd ? h->celldata.p : nullptr;
       a.pix_bytes = h->pix_bytes;
       const dim3 blocks((g.Wx + 31) / 32, (g.Y + kFaceThreads / 32 - 1) / (kFaceThreads / 32), h->zs1 - h->zs0);
@@ -792,6 +831,7 @@ int cub_device_buffers(cub_handle h, const float** points, const void** cells, c
 int cub_debug_bitmask(cub_handle h, uint32_t* out, uint64_t* words_per_row) {
   if (!h) return CUB_ERR_INVALID;
   if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_debug_bitmask before cub_count");
+  if (h->pad) return fail(h, CUB_ERR_UNSUPPORTED, "cub_debug_bitmask: the bitmask of image_border_faces runs is that of the padded image");
   if (words_per_row) *words_per_row = (uint64_t)h->g.Wp;
   if (out) {
     CU_TRY(h, cudaSetDevice(h->device));

@@ -143,4 +143,28 @@ __global__ void __launch_bounds__(256) k_classify_packed(const T* __restrict__ v
   }
 }
 
+// ---- image_border_faces: the bitmask of the image padded with one outside layer ---------------------------
+// Bit (x', y', z') of the padded grid is voxel (x'-1, y'-1, z'-zpad) of the buffer, or 0 (outside) beyond it.
+// Every later kernel runs unchanged on the padded grid: its clamped neighbours at the padded border are outside
+// on both sides, so no face is lost and none is invented.  One warp per 32-voxel word; the loads are one
+// element off the 128-byte alignment, which costs this opt-in mode a few percent of bandwidth.
+template <typename T>
+__global__ void __launch_bounds__(256) k_classify_padded(const T* __restrict__ vol, uint32_t* __restrict__ bits, Grid gb,
+                                                         int vX, int vY, int vZl, int zpad, T iso, unsigned n_words_total) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warp0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (unsigned task = warp0; task < n_words_total; task += n_warps) {
+    const unsigned row = task / (unsigned)gb.Wx;       // padded row index: zb * gb.Y + yb
+    const int w = (int)(task - row * (unsigned)gb.Wx);
+    const int zb = (int)(row / (unsigned)gb.Y), yb = (int)(row - (unsigned)zb * (unsigned)gb.Y);
+    const int x = 32 * w + lane - 1, y = yb - 1, z = zb - zpad;
+    bool in = false;
+    if (x >= 0 && x < vX && y >= 0 && y < vY && z >= 0 && z < vZl)
+      in = !(__ldcs(vol + ((size_t)z * vY + y) * vX + x) < iso);
+    const uint32_t word = __ballot_sync(0xffffffffu, in);
+    if (lane == 0) bits[(size_t)row * gb.Wp + w] = word;
+  }
+}
+
 }  // namespace cub

@@ -28,6 +28,7 @@ struct FaceArgs {
   void* cells;                 // final cells (IdT) or scratch quads (uint32 scan-relative ids)
   int mode;                    // kEmit*
   const void* vol;             // for cell data (may be null)
+  int vX, vY, vpad, vzpad;     // cell data: buffer row / slice size; lattice (x, y, z) is voxel (x - vpad, y - vpad, z - vzpad)
   void* celldata;
   int pix_bytes;
 };
@@ -231,7 +232,8 @@ __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
     }
     // the voxel behind the face (cell data): word src of this warp's row
     const unsigned long long voxel =
-        a.celldata ? load_pixel(a.vol, ((size_t)zl * g.Y + y) * g.X + (size_t)(blockIdx.x * 32 + src) * 32 + b, a.pix_bytes) : 0ull;
+        a.celldata ? load_pixel(a.vol, ((size_t)(zl - a.vzpad) * a.vY + (size_t)(y - a.vpad)) * a.vX +
+                                           (size_t)((blockIdx.x * 32 + src) * 32 + b - a.vpad), a.pix_bytes) : 0ull;
     if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }

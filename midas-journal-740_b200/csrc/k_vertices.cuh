@@ -27,7 +27,8 @@ struct VertexArgs {
   const uint32_t* cofs;
   int EY, EW;
   int plane_lo, plane_hi;   // local corner planes that faces of this handle reference (inclusive)
-  int zg0;                  // global z of local plane 0
+  int zg0;                  // image z index of local corner plane 0
+  int cpad;                 // 1 if the lattice is that of the padded image (image_border_faces): image x, y = lattice - 1
   Geom geom;
   float* points;            // indexed by scan-relative vertex id
   uint32_t* perm;           // [active corners of planes plane_lo..plane_hi] -> scan-relative vertex id
@@ -97,8 +98,8 @@ __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
     const int cx = (int)(v[j] & 0xffffu), cy = (int)((v[j] >> 16) & 0x7fffu);
     if (id >= a.first_point) {
       float* p = a.points + 3 * id;
-      p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], cx);
-      p[1] = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy);
+      p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], cx - a.cpad);
+      p[1] = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy - a.cpad);
       p[2] = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz[j] + a.zg0);
     }
     if (cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
@@ -115,7 +116,7 @@ struct RasterPointArgs {
   const uint32_t* cofs;
   int EY, EW, Wc;
   int plane_lo, plane_hi;   // local corner planes to emit (inclusive)
-  int zg0;
+  int zg0, cpad;            // as in VertexArgs
   Geom geom;
   float* points;            // indexed by slot
 };
@@ -128,13 +129,13 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
   uint32_t m = __ldg(a.act + e);
   if (!m) return;
   uint32_t id = __ldg(a.cofs + e);
-  const float py = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy);
+  const float py = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy - a.cpad);
   const float pz = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz + a.zg0);
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;
     float* p = a.points + 3 * (size_t)id++;
-    p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], 32 * w + b);
+    p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], 32 * w + b - a.cpad);
     p[1] = py;
     p[2] = pz;
   }

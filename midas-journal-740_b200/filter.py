@@ -51,6 +51,7 @@ class CuberilleImageToMeshFilter:
         self._project = True
         self._cell_data = False
         self._raster_order = False
+        self._border_faces = False
         self._thr = 0.5
         self._step = -1.0
         self._relax = 0.95
@@ -97,6 +98,8 @@ class CuberilleImageToMeshFilter:
     def SavePixelAsCellDataOn(self): self.SetSavePixelAsCellData(True)
     def SavePixelAsCellDataOff(self): self.SetSavePixelAsCellData(False)
     # extension: number the vertices in lattice-corner raster order instead of the reference's creation order
+    def SetImageBorderFaces(self, b): self._set("_border_faces", bool(b))   # opt-in closed mesh (txx:133 TODO)
+    def GetImageBorderFaces(self): return self._border_faces
     def SetRasterVertexOrder(self, b): self._set("_raster_order", bool(b))
     def GetRasterVertexOrder(self): return self._raster_order
 
@@ -124,6 +127,7 @@ class CuberilleImageToMeshFilter:
         p.project_vertices = int(self._project)
         p.save_pixel_as_cell_data = int(self._cell_data)
         p.vertex_order = capi.ORDER_RASTER if self._raster_order else capi.ORDER_REFERENCE
+        p.image_border_faces = int(self._border_faces)
         p.surface_distance_threshold = self._thr
         p.step_length = self._step
         p.step_relaxation = self._relax

@@ -57,7 +57,8 @@ struct orc_params {
   double step_length;  // <0: auto (txx:82-85)
   double step_relaxation;
   uint32_t max_steps;
-  uint32_t reserved;
+  uint32_t image_border_faces;  // 0: the reference (clamped neighbours: no face on the image border);
+                                // 1: a neighbour outside the image is outside the surface (closed mesh, txx:133 TODO)
 };
 
 struct orc_mesh {
@@ -322,7 +323,11 @@ struct Runner {
     for (int i = 0; i < 6; ++i) faceHasQuad[i] = false;
     for (int i = 0; i < 8; ++i) vertexHasQuad[i] = false;
     for (int i = 0; i < 6; ++i) {
-      faceHasQuad[i] = vol.at_clamped(x + kFaceOffset[i][0], y + kFaceOffset[i][1], z + kFaceOffset[i][2]) < iso;
+      const int64_t nx = x + kFaceOffset[i][0], ny = y + kFaceOffset[i][1], nz = z + kFaceOffset[i][2];
+      if (P.image_border_faces && (nx < 0 || ny < 0 || nz < 0 || nx >= vol.g.nx || ny >= vol.g.ny || nz >= vol.g.nz))
+        faceHasQuad[i] = true;  // opt-in: what padding the image with one outside layer would give
+      else
+        faceHasQuad[i] = vol.at_clamped(nx, ny, nz) < iso;
       if (faceHasQuad[i]) {
         ++numFaces;
         for (int k = 0; k < 4; ++k) vertexHasQuad[kFaceCorners[i][k]] = true;  // SetVerticesFromFace

@@ -76,6 +76,54 @@ def test_extreme_aspect_ratios(shape):
         assert_mesh_equal(run_filter(vol, iso, triangles=tri, project=False), ref, f"{shape} tri={tri}")
 
 
+@pytest.mark.parametrize("dtype,shape,fill", [(np.uint8, (6, 7, 8), 0.5), (np.int16, (9, 33, 65), 0.5), (np.float32, (12, 40, 200), 0.8),
+                                              (np.uint8, (1, 1, 1), 0.9), (np.uint8, (3, 4, 5), 1.0), (np.uint16, (5, 2, 130), 0.6)])
+def test_image_border_faces(dtype, shape, fill):
+    """opt-in closed mesh: the image padded with one outside layer (bit-exact against the oracle's flag)"""
+    O = oracle()
+    vol, iso = random_volume(shape, dtype, seed=shape[2] + 3, fill=fill)
+    if fill >= 1.0:
+        vol[...] = np.asarray(iso).astype(vol.dtype)  # everything inside: a closed box
+    for tri, cd in ((False, False), (True, True)):
+        ref = O.cuberille(vol, iso, triangles=tri, project=False, cell_data=cd, mode=O.CLOSED_FORM, border_faces=True)
+        mesh = run_filter(vol, iso, triangles=tri, project=False, cell_data=cd, border_faces=True)
+        assert_mesh_equal(mesh, ref, f"border faces {np.dtype(dtype).name} {shape} tri={tri}")
+        assert ref.cells.shape[0] > 0
+
+
+def test_image_border_faces_with_projection_slabs_and_raster_order():
+    P, O = pkg(), oracle()
+    vol = gyroid((41, 30, 50), 13.0, border=False)
+    ref = O.cuberille(vol, 0.0, triangles=True, project=True, thr=0.01, mode=O.CLOSED_FORM, border_faces=True,
+                      spacing=(0.5, 1.0, 2.0), origin=(3.0, -2.0, 7.0))
+    mesh = run_filter(P.Image(vol, (0.5, 1.0, 2.0), (3.0, -2.0, 7.0)), 0.0, triangles=True, project=True, thr=0.01, border_faces=True)
+    assert_mesh_equal(mesh, ref, "border faces + projection")
+    img = P.Image(vol, (0.5, 1.0, 2.0), (3.0, -2.0, 7.0))
+    ras = run_filter(img, 0.0, triangles=True, project=True, thr=0.01, border_faces=True, raster_order=True)
+    ras0 = run_filter(img, 0.0, triangles=True, project=False, border_faces=True, raster_order=True)
+    ref0 = O.cuberille(vol, 0.0, triangles=True, project=False, mode=O.CLOSED_FORM, border_faces=True,
+                       spacing=(0.5, 1.0, 2.0), origin=(3.0, -2.0, 7.0))
+    assert_mesh_equal_up_to_vertex_order(ras, ref, ras0, ref0, "border faces + raster order")
+    # z-slabs
+    nz = vol.shape[0]
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices, p.surface_distance_threshold, p.image_border_faces = 0.0, 1, 1, 0.01, 1
+    pts, cells, pbase, cbase = [], [], 0, 0
+    for z0, z1 in ((0, 13), (13, 14), (14, 30), (30, 41)):
+        lo, hi = max(0, z0 - 9), min(nz, z1 + 9)
+        h = P.capi.Handle(0)
+        h.set_volume(vol[lo:hi], (0.5, 1.0, 2.0), (3.0, -2.0, 7.0))  # the IMAGE origin: the slab offset comes from set_slab
+        h.set_slab(nz, lo, z0, z1)
+        n_pts, n_quads = h.count(p)
+        h.set_id_base(pbase, cbase)
+        h.emit(4)
+        a, b, _ = h.fetch()
+        pts.append(a); cells.append(b)
+        pbase += n_pts; cbase += 2 * n_quads
+        h.close()
+    assert_mesh_equal(P.Mesh(np.concatenate(pts), np.concatenate(cells)), ref, "border faces + slabs")
+
+
 def test_assign_by_second_sweep_gives_the_same_mesh(monkeypatch):
     """CUB_ASSIGN_SWEEP=1: K3a recomputes the ownership masks in a second sweep instead of reading the ones K2a
     stored (32 B of scratch per lattice entry less)"""

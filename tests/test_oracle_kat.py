@@ -121,3 +121,22 @@ def test_projection_moves_vertices_towards_the_iso_value():
     assert np.mean(np.abs(v1 - 15) < 0.2) > 0.95
     assert np.mean(np.abs(v1 - 15)) < np.mean(np.abs(v0 - 15))
     assert np.max(np.linalg.norm(m1.points - m0.points, axis=1)) < 5.0
+
+
+def test_image_border_faces_close_the_mesh():
+    """opt-in: a neighbour outside the image is outside the surface (what padding with one outside layer gives);
+    the reference never makes a face on the image border (h:55-57, txx:133)"""
+    O = oracle()
+    box = np.full((3, 4, 5), 9, np.uint8)  # everything inside
+    for mode in (O.LITERAL, O.CLOSED_FORM):
+        assert O.cuberille(box, 5, triangles=False, project=False, mode=mode).cells.shape[0] == 0
+        m = O.cuberille(box, 5, triangles=False, project=False, mode=mode, border_faces=True)
+        assert m.cells.shape[0] == 2 * (3 * 4 + 4 * 5 + 3 * 5) and m.points.shape[0] == 6 * 5 * 4 - 4 * 3 * 2
+    # equals the default run on the explicitly padded volume, up to the shift of the origin
+    rng = np.random.default_rng(11)
+    vol = rng.integers(0, 256, size=(6, 7, 9), dtype=np.uint8)
+    padded = np.zeros((8, 9, 11), np.uint8)
+    padded[1:-1, 1:-1, 1:-1] = vol
+    a = O.cuberille(vol, 128, triangles=True, project=False, mode=O.CLOSED_FORM, border_faces=True)
+    b = O.cuberille(padded, 128, triangles=True, project=False, mode=O.CLOSED_FORM, origin=(-1.0, -1.0, -1.0))
+    assert np.array_equal(a.cells, b.cells) and np.array_equal(a.points, b.points)

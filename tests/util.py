@@ -57,16 +57,17 @@ def read_fixture(name: str):
 
 
 def gyroid(n, period=16.0, dtype=np.float32, border=-2.0):
-    """gyroid field on integer voxel coordinates, shape (nz, ny, nx), outermost layer forced outside"""
+    """gyroid field on integer voxel coordinates, shape (nz, ny, nx), outermost layer forced outside (`border`)"""
     nz, ny, nx = (n, n, n) if np.isscalar(n) else n
     k = np.float32(2.0 * np.pi / period)
     z, y, x = np.meshgrid(np.arange(nz, dtype=np.float32), np.arange(ny, dtype=np.float32),
                           np.arange(nx, dtype=np.float32), indexing="ij")
     g = np.sin(k * x) * np.cos(k * y) + np.sin(k * y) * np.cos(k * z) + np.sin(k * z) * np.cos(k * x)
     g = g.astype(dtype)
-    g[0], g[-1] = border, border
-    g[:, 0], g[:, -1] = border, border
-    g[:, :, 0], g[:, :, -1] = border, border
+    if border is not False:  # (False: the field runs up to the image border, for image_border_faces)
+        g[0], g[-1] = border, border
+        g[:, 0], g[:, -1] = border, border
+        g[:, :, 0], g[:, :, -1] = border, border
     return np.ascontiguousarray(g)
 
 
@@ -102,7 +103,7 @@ def smooth_volume(shape, dtype, seed, scale=60.0):
 
 
 def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5, step=-1.0, relax=0.95, max_steps=50,
-               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), raster_order=False):
+               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), raster_order=False, border_faces=False):
     """Drive the CUDA path through the filter mirror, with the reference driver's call sequence
     (Testing/CuberilleTest01.cxx:144-162)."""
     P = pkg()
@@ -114,6 +115,7 @@ def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5,
     f.SetProjectVerticesToIsoSurface(project)
     f.SetSavePixelAsCellData(cell_data)
     f.SetRasterVertexOrder(raster_order)
+    f.SetImageBorderFaces(border_faces)
     f.SetProjectVertexSurfaceDistanceThreshold(thr)
     if step >= 0:
         f.SetProjectVertexStepLength(step)
