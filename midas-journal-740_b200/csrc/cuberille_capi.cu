@@ -740,11 +740,17 @@ int cub_emit(cub_handle h, int id_bytes) {
       a.celldata = cd ? h->celldata.p : nullptr;
       a.pix_bytes = h->pix_bytes;
       const dim3 blocks((g.Wx + 31) / 32, (g.Y + kFaceThreads / 32 - 1) / (kFaceThreads / 32), h->zs1 - h->zs0);
-      if (mode == kEmitScratchQuads) k_faces<uint32_t, kEmitScratchQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
-      else if (mode == kEmitQuads && id_bytes == 4) k_faces<uint32_t, kEmitQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
-      else if (mode == kEmitQuads) k_faces<unsigned long long, kEmitQuads><<<blocks, kFaceThreads, 0, h->stream>>>(a);
-      else if (id_bytes == 4) k_faces<uint32_t, kEmitTrisFixed><<<blocks, kFaceThreads, 0, h->stream>>>(a);
-      else k_faces<unsigned long long, kEmitTrisFixed><<<blocks, kFaceThreads, 0, h->stream>>>(a);
+#define CUB_FACES(IdT, MODE)                                                                   \
+      do {                                                                                       \
+        if (cd) k_faces<IdT, MODE, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);             \
+        else k_faces<IdT, MODE, false><<<blocks, kFaceThreads, 0, h->stream>>>(a);               \
+      } while (0)
+      if (mode == kEmitScratchQuads) CUB_FACES(uint32_t, kEmitScratchQuads);
+      else if (mode == kEmitQuads && id_bytes == 4) CUB_FACES(uint32_t, kEmitQuads);
+      else if (mode == kEmitQuads) CUB_FACES(unsigned long long, kEmitQuads);
+      else if (id_bytes == 4) CUB_FACES(uint32_t, kEmitTrisFixed);
+      else CUB_FACES(unsigned long long, kEmitTrisFixed);
+#undef CUB_FACES
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     }

@@ -108,7 +108,7 @@ struct FaceSmem {
 // One thread per 32-voxel word computes the face masks; the surface voxels of a warp's 32 words are then
 // compacted into a queue and handled one per lane, so a word with ten surface voxels does not stall the 31
 // lanes whose words have none.
-template <typename IdT, int MODE>
+template <typename IdT, int MODE, bool CD>
 __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   const Grid& g = a.g;
@@ -232,14 +232,14 @@ __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
     }
     // the voxel behind the face (cell data): word src of this warp's row
     const unsigned long long voxel =
-        a.celldata ? load_pixel(a.vol, ((size_t)(zl - a.vzpad) * a.vY + (size_t)(y - a.vpad)) * a.vX +
+        CD ? load_pixel(a.vol, ((size_t)(zl - a.vzpad) * a.vY + (size_t)(y - a.vpad)) * a.vX +
                                            (size_t)((blockIdx.x * 32 + src) * 32 + b - a.vpad), a.pix_bytes) : 0ull;
-    if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f3) { write_cell<IdT, MODE>(a, fi, vid[2], vid[3], vid[7], vid[6]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f4) { write_cell<IdT, MODE>(a, fi, vid[0], vid[3], vid[2], vid[1]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f5) { write_cell<IdT, MODE>(a, fi, vid[4], vid[5], vid[6], vid[7]); if (a.celldata) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f3) { write_cell<IdT, MODE>(a, fi, vid[2], vid[3], vid[7], vid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f4) { write_cell<IdT, MODE>(a, fi, vid[0], vid[3], vid[2], vid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f5) { write_cell<IdT, MODE>(a, fi, vid[4], vid[5], vid[6], vid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
   }
 }
 
