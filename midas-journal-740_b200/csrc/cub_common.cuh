@@ -6,11 +6,11 @@
 //              ( inside == !(v < iso), txx:139-141 ).  Wp = roundup(ceil(X/32), 4) so every
 //              row is 16-byte aligned; bits x >= X of the last valid word replicate bit X-1
 //              (that makes the +x edge-replicate of txx:167 a plain shift); pad words are 0.
-//   vofs/fofs: [Zl][Y][Wp] uint32, exclusive prefix (in voxel-raster order over the scan
-//              range) of the number of corner vertices OWNED / quads EMITTED by the voxels
-//              before this word.
-//
-//   counts   : [Zl][Y][Wp] uint32, faces << 16 | owned corners of the word (K2a -> K2b)
+//   lattice  : [Zl+1][Y+1][EW] uint32 entries, one per corner word (EW = roundup(ceil((X+1)/32)+1, 4)); entry
+//              (z, y, w) also stands for voxel word w of row y of slice z.  K2a writes cnt (owned corners |
+//              faces << 10 | active corners << 20), act (active-corner mask) and own (the 8 ownership masks);
+//              K2b turns cnt into vofs / fofs / cofs, the exclusive prefixes (in raster order over the scan
+//              range) of owned corners, faces and active corners.
 //
 // The reference keeps a std::map per corner plane (h:243-313) to find out whether a corner
 // already has a vertex.  Here ownership is a closed form of the 2x2x2 inside bits around a corner:

@@ -5,8 +5,9 @@
 // (txx:279-332).  Cell ids follow voxel raster x face index (nextCellId, txx:117): cell index =
 // fofs[word] + rank inside the word.  The four vertex ids of a face come from the corner -> id map:
 //     slot(corner) = cofs[corner word] + popc(act[corner word] & bits below)      id = perm[slot]
-// where the <= 8 corner words around the voxel word are loaded once per word.  No shared memory, no
-// synchronisation: words without faces (most of them) exit after seven bitmask loads.
+// where the corner words around the voxel word are loaded once per word, up front together with the bitmask
+// words (the kernel is bound by its chain of dependent loads, not by bytes).  The surface voxels of a warp's
+// 32 words are then compacted into a shared-memory queue and emitted one voxel per lane.
 #pragma once
 #include "cub_common.cuh"
 

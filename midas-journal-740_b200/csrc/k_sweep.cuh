@@ -22,8 +22,9 @@
 // closed form for corner plane z+1, publishes what its -x / -y neighbours need (6 words per thread,
 // whatever R), and assembles the 8 ownership masks of its R voxel words in slice z.
 //   MODE_COUNT  (K2a): per entry of the [Zl+1][Y+1][EW] lattice one packed count
-//                      (owned corners | faces << 10 | active corners << 20) and the active-corner mask
-//   MODE_ASSIGN (K3a): walks the owned corners of every voxel word in reference order (voxel bit, then local
+//                      (owned corners | faces << 10 | active corners << 20), the active-corner mask and, for
+//                      words that own a corner, the 8 ownership masks themselves (k_assign.cuh walks them)
+//   MODE_ASSIGN (K3a, first version, kept behind CUB_ASSIGN_SWEEP=1): a second sweep that walks the owned corners of every voxel word in reference order (voxel bit, then local
 //                      corner 0..7, txx:179-194) and records, at vertex id = vofs[word] + rank, WHICH lattice
 //                      corner that vertex is (packed coordinates); k_vertices.cuh turns that into points and
 //                      the corner -> id map the face kernel reads
