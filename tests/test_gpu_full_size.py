@@ -106,3 +106,91 @@ def test_full_size_properties(kind, size, p0, iso):
     assert_mesh_equal(P.Mesh(sp, sc), ref, f"{kind} sub-slab")
     hs2.close()
     h.close()
+
+
+def test_headline_size_gyroid_1024_on_device():
+    """BASELINE.json's headline workload (gyroid 1024^3 float32, P = 128, quads, u32 ids) checked where it lives:
+    the mesh stays on the device and torch does the set arithmetic (44 M points, 44 M quads).
+    * ids dense and all used; every quad a unit square on the half-integer lattice
+    * closed surface (the generator forces the border outside): even edge multiplicities <= 4, sum = 4 F
+    * idempotent; 4 z-slabs concatenate to the same bytes
+    * a 16-slice sub-slab of the same bytes goes through the oracle, bit for bit (triangles + projection)"""
+    import torch
+    P = pkg()
+    S = 1024
+    dev = torch.device("cuda:0")
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = 0.0, 0, 0
+
+    def run(handle):
+        n_pts, n_quads = handle.count(p)
+        return n_pts, n_quads
+
+    def fetch(handle, n_pts, n_quads):
+        pts = torch.empty((n_pts, 3), dtype=torch.float32, device=dev)
+        cells = torch.empty((n_quads, 4), dtype=torch.int32, device=dev)
+        handle.fetch_into(pts.data_ptr(), cells.data_ptr(), 0, P.capi.MEM_DEVICE)
+        return pts, cells
+
+    h = P.capi.Handle(0)
+    h.generate(P.capi.GEN_GYROID, (S, S, S), p0=128.0)
+    n_pts, n_quads = run(h)
+    h.emit(4)
+    pts, quads = fetch(h, n_pts, n_quads)
+    assert n_pts > 40_000_000 and n_quads > 40_000_000
+    q = quads.long()
+    assert int(q.max()) == n_pts - 1 and int(q.min()) == 0
+    assert bool((torch.bincount(q.reshape(-1), minlength=n_pts) > 0).all())
+    assert torch.equal(pts + 0.5, torch.round(pts + 0.5))
+    for k in range(4):  # unit squares: consecutive corners differ by one lattice step along one axis
+        d = (pts[q[:, k]] - pts[q[:, (k + 1) % 4]]).abs().sum(dim=1)
+        assert bool((d == 1.0).all())
+        del d
+    lo = torch.minimum(q, q.roll(-1, dims=1))
+    hi = torch.maximum(q, q.roll(-1, dims=1))
+    keys = (lo << 32 | hi).reshape(-1)
+    del lo, hi
+    _, mult = torch.unique(keys, return_counts=True)
+    del keys
+    assert int(mult.sum()) == 4 * n_quads and bool((mult % 2 == 0).all()) and int(mult.max()) <= 4
+    del mult, q
+    # idempotence
+    assert run(h) == (n_pts, n_quads)
+    h.emit(4)
+    pts2, quads2 = fetch(h, n_pts, n_quads)
+    assert torch.equal(pts.view(torch.int32), pts2.view(torch.int32)) and torch.equal(quads, quads2)
+    del pts2, quads2
+    # oracle anchor on a sub-slab of the same bytes
+    vol = h.download_volume()
+    sub = np.ascontiguousarray(vol[500:516])
+    del vol
+    h.close()
+    O = oracle()
+    ref = O.cuberille(sub, 0.0, triangles=True, project=True, thr=0.01)
+    hs = P.capi.Handle(0)
+    hs.set_volume(sub)
+    ps = P.capi.default_params()
+    ps.iso_value, ps.surface_distance_threshold = 0.0, 0.01
+    hs.run(ps)
+    sp, sc, _ = hs.fetch()
+    assert_mesh_equal(P.Mesh(sp, sc), ref, "gyroid 1024 sub-slab")
+    hs.close()
+    # 4 z-slabs, generated per slab with a 2-slice halo
+    pbase = cbase = 0
+    for s in range(4):
+        z0, z1 = S * s // 4, S * (s + 1) // 4
+        lo_, hi_ = max(0, z0 - 2), min(S, z1 + 2)
+        hh = P.capi.Handle(0)
+        hh.generate(P.capi.GEN_GYROID, (S, S, hi_ - lo_), (S, S, S), lo_, 128.0)
+        hh.set_slab(S, lo_, z0, z1)
+        np_, nq = hh.count(p)
+        hh.set_id_base(pbase, cbase)
+        hh.emit(4)
+        a, b = fetch(hh, np_, nq)
+        assert torch.equal(a.view(torch.int32), pts[pbase:pbase + np_].view(torch.int32)), f"slab {s}: points"
+        assert torch.equal(b, quads[cbase:cbase + nq]), f"slab {s}: cells"
+        pbase += np_
+        cbase += nq
+        hh.close()
+        del a, b
+    assert (pbase, cbase) == (n_pts, n_quads)
