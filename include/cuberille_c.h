@@ -112,6 +112,14 @@ int cub_set_volume(cub_handle h, const void *data, int dtype, const uint64_t dim
                    const double spacing[3], const double origin[3],
                    const double direction[9], int mem_kind);
 
+/* Image index of the buffer's first voxel (itk::ImageRegion::GetIndex of the
+ * buffered region; every test of the reference has 0).  The points are
+ * TransformIndexToPhysicalPoint(index + region index) (txx:266) and the
+ * interpolators' continuous indices are image indices.  Call after
+ * cub_set_volume (which resets it to 0).  For a z-slab it is the index of the
+ * WHOLE image's first voxel.                                                   */
+int cub_set_region_index(cub_handle h, const int64_t index[3]);
+
 /* z-slab decomposition (no counterpart in the reference: GenerateData is a
  * single raster loop txx:136-206; concatenating z-slabs preserves its order).
  *   image_nz      : z size of the WHOLE image

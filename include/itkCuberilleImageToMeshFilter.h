@@ -22,8 +22,8 @@
  *  - TInterpolator must be itk::LinearInterpolateImageFunction<TInputImage>
  *    (the device kernel implements ITK's trilinear interpolation; another
  *    interpolator type raises an exception instead of being silently ignored);
- *  - the image direction must be the identity and the buffered region must start
- *    at index 0 (exception otherwise);
+ *  - the image direction must be the identity (exception otherwise); a buffered
+ *    region that does not start at index 0 is passed on (cub_set_region_index);
  *  - a zero image gradient stops a vertex instead of dividing by zero (txx:452),
  *    out-of-image interpolation reads are clamped instead of undefined.
  *=========================================================================*/
@@ -213,14 +213,12 @@ protected:
     // image geometry (txx:75-79, 266-270)
     const typename InputImageType::RegionType region = image->GetBufferedRegion();
     uint64_t dims[3];
+    int64_t regionIndex[3];
     double spacing[3], origin[3], direction[9];
     double maxSpacing = 0.0;
     for ( unsigned int i = 0; i < 3; i++ )
       {
-      if ( region.GetIndex()[i] != 0 )
-        {
-        itkExceptionMacro( << "the buffered region must start at index 0" );
-        }
+      regionIndex[i] = static_cast<int64_t>( region.GetIndex()[i] );  // TransformIndexToPhysicalPoint sees it (txx:266)
       dims[i] = region.GetSize()[i];
       spacing[i] = image->GetSpacing()[i];
       origin[i] = image->GetOrigin()[i];
@@ -244,6 +242,7 @@ protected:
     this->Check( cub_set_volume( m_Handle, image->GetBufferPointer(),
                                  cuberille_detail::PixelCode<InputPixelType>::value,
                                  dims, spacing, origin, direction, CUB_MEM_HOST ) );
+    this->Check( cub_set_region_index( m_Handle, regionIndex ) );
     cub_params params;
     cub_default_params( &params );
     params.iso_value = static_cast<double>( m_IsoSurfaceValue );

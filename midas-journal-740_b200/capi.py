@@ -26,7 +26,7 @@ CODE_DTYPES = {v: k for k, v in DTYPE_CODES.items()}
 # every symbol include/cuberille_c.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "cub_abi_version", "cub_default_params", "cub_create", "cub_destroy", "cub_last_error", "cub_set_volume",
-    "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit_vertices", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
+    "cub_set_region_index", "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit_vertices", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
     "cub_synchronize", "cub_device_buffers",
     "cub_debug_bitmask", "cub_debug_project_points", "cub_generate_volume", "cub_download_volume",
     "cub_enable_timing", "cub_get_timings", "cub_launch_count",
@@ -82,6 +82,8 @@ def load() -> C.CDLL:
     L.cub_last_error.argtypes = [vp]
     L.cub_set_volume.restype = i
     L.cub_set_volume.argtypes = [vp, vp, i, pu64, pd, pd, pd, i]
+    L.cub_set_region_index.restype = i
+    L.cub_set_region_index.argtypes = [vp, C.POINTER(C.c_int64)]
     L.cub_set_slab.restype = i
     L.cub_set_slab.argtypes = [vp, u64, u64, u64, u64]
     L.cub_count.restype = i
@@ -174,6 +176,10 @@ class Handle:
         og = (C.c_double * 3)(*origin)
         self._check(self._L.cub_set_volume(self._h, C.c_void_p(ptr), DTYPE_CODES[np.dtype(dtype)], dims, sp, og, None, mem_kind))
         self.dtype, self.dims = np.dtype(dtype), tuple(dims_xyz)
+
+    def set_region_index(self, index_xyz):
+        """Image index of the buffer's first voxel (after set_volume, which resets it to 0)."""
+        self._check(self._L.cub_set_region_index(self._h, (C.c_int64 * 3)(*[int(v) for v in index_xyz])))
 
     def set_slab(self, image_nz: int, local_z0: int, own_z0: int, own_z1: int):
         self._check(self._L.cub_set_slab(self._h, image_nz, local_z0, own_z0, own_z1))

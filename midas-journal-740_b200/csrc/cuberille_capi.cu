@@ -120,6 +120,7 @@ struct cub_handle_s {
   cub_params params{};
   Grid g{};    // the lattice every kernel after K1 works on: the buffer, or (image_border_faces) the buffer padded by one layer
   Grid gv{};   // the voxel buffer itself (K1, K4, cell data)
+  long long i0[3] = {0, 0, 0};  // image index of buffer voxel (0, 0, 0): cub_set_region_index
   int pad = 0, zpad_lo = 0;  // image_border_faces: lattice (x, y, z) is voxel (x - pad, y - pad, z - zpad_lo)
   bool counted = false, emitted = false;
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
@@ -295,6 +296,7 @@ int launch_project(cub_handle h, float* pts, size_t n) {
   a.vol = h->d_vol;
   a.g = h->gv;
   a.geom = h->geom;
+  for (int k = 0; k < 3; ++k) a.i0[k] = h->i0[k];
   a.iso = iso_as_pixel(h->dtype, h->params.iso_value);
   a.thr = h->params.surface_distance_threshold;
   a.step0 = h->step_used;
@@ -439,6 +441,7 @@ static int set_geometry(cub_handle h, int dtype, const uint64_t dims[3], const d
   }
   h->dtype = dtype;
   h->pix_bytes = pb;
+  h->i0[0] = h->i0[1] = h->i0[2] = 0;
   h->image_nz = dims[2];
   h->local_z0 = 0;
   h->own_z0 = 0;
@@ -465,6 +468,18 @@ int cub_set_volume(cub_handle h, const void* data, int dtype, const uint64_t dim
     return fail(h, CUB_ERR_INVALID, "bad mem_kind %d", mem_kind);
   }
   h->has_volume = true;
+  return CUB_OK;
+}
+
+int cub_set_region_index(cub_handle h, const int64_t index[3]) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->has_volume) return fail(h, CUB_ERR_INVALID, "cub_set_region_index before cub_set_volume");
+  for (int k = 0; k < 3; ++k) {
+    const long long v = index ? (long long)index[k] : 0;
+    if (v < -(1ll << 40) || v > (1ll << 40)) return fail(h, CUB_ERR_INVALID, "region index out of range");
+    h->i0[k] = v;
+  }
+  h->counted = h->emitted = false;
   return CUB_OK;
 }
 
@@ -671,7 +686,8 @@ static int emit_vertex_stage(cub_handle h) {
       a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
-      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.zg0 = g.zg0 - h->pad; a.cpad = h->pad; a.geom = h->geom;
+      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
+      a.coff[0] = h->i0[0] - h->pad; a.coff[1] = h->i0[1] - h->pad; a.coff[2] = h->i0[2] + g.zg0 - h->pad;
       a.points = h->points.p; a.perm = h->perm.p;
       k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
       h->launches++;
@@ -682,7 +698,8 @@ static int emit_vertex_stage(cub_handle h) {
     RasterPointArgs a{};
     a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
     a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
-    a.zg0 = g.zg0 - h->pad; a.cpad = h->pad; a.geom = h->geom; a.points = h->points.p;
+    a.coff[0] = h->i0[0] - h->pad; a.coff[1] = h->i0[1] - h->pad; a.coff[2] = h->i0[2] + g.zg0 - h->pad;
+    a.geom = h->geom; a.points = h->points.p;
     const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
     k_points_raster<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;

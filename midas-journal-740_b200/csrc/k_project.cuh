@@ -31,6 +31,7 @@ struct ProjArgs {
   unsigned max_steps;
   float* points;
   size_t n_points;
+  long long i0[3];           // image index of buffer voxel (0, 0, 0) (cub_set_region_index): continuous indices are image indices
   unsigned long long* work;  // device counter (zeroed before the launch): next vertex to hand out
 };
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     for (int k = 0; k < 3; ++k) {
       const double ci = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
       const double f = floor(ci);
-      base[k] = (long long)f;
+      base[k] = (long long)f - a.i0[k];  // buffer-relative
       dist[k] = ci - f;
     }
     if (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2]) {

@@ -27,8 +27,7 @@ struct VertexArgs {
   const uint32_t* cofs;
   int EY, EW;
   int plane_lo, plane_hi;   // local corner planes that faces of this handle reference (inclusive)
-  int zg0;                  // image z index of local corner plane 0
-  int cpad;                 // 1 if the lattice is that of the padded image (image_border_faces): image x, y = lattice - 1
+  long long coff[3];        // image index of lattice corner (0, 0, 0): slab offset, region index, minus the pad of image_border_faces
   Geom geom;
   float* points;            // indexed by scan-relative vertex id
   uint32_t* perm;           // [active corners of planes plane_lo..plane_hi] -> scan-relative vertex id
@@ -98,9 +97,9 @@ __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
     const int cx = (int)(v[j] & 0xffffu), cy = (int)((v[j] >> 16) & 0x7fffu);
     if (id >= a.first_point) {
       float* p = a.points + 3 * id;
-      p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], cx - a.cpad);
-      p[1] = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy - a.cpad);
-      p[2] = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz[j] + a.zg0);
+      p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], cx + a.coff[0]);
+      p[1] = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy + a.coff[1]);
+      p[2] = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz[j] + a.coff[2]);
     }
     if (cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
       const uint32_t below = (1u << (cx & 31)) - 1u;
@@ -116,7 +115,7 @@ struct RasterPointArgs {
   const uint32_t* cofs;
   int EY, EW, Wc;
   int plane_lo, plane_hi;   // local corner planes to emit (inclusive)
-  int zg0, cpad;            // as in VertexArgs
+  long long coff[3];        // as in VertexArgs
   Geom geom;
   float* points;            // indexed by slot
 };
@@ -129,13 +128,13 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
   uint32_t m = __ldg(a.act + e);
   if (!m) return;
   uint32_t id = __ldg(a.cofs + e);
-  const float py = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy - a.cpad);
-  const float pz = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz + a.zg0);
+  const float py = corner_coord(a.geom.spacing[1], a.geom.origin[1], cy + a.coff[1]);
+  const float pz = corner_coord(a.geom.spacing[2], a.geom.origin[2], cz + a.coff[2]);
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;
     float* p = a.points + 3 * (size_t)id++;
-    p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], 32 * w + b - a.cpad);
+    p[0] = corner_coord(a.geom.spacing[0], a.geom.origin[0], 32 * w + b + a.coff[0]);
     p[1] = py;
     p[2] = pz;
   }

@@ -143,6 +143,7 @@ class CuberilleImageToMeshFilter:
         if self._step < 0.0:
             self._step = max(img.spacing) * 0.25  # sticky, txx:82-85
         self._handle.set_volume(img.data, img.spacing, img.origin, img.direction)
+        self._handle.set_region_index(getattr(img, "region_index", (0, 0, 0)))
         self._handle.run(self.params(), self._id_bytes)
         pts, cells, cd = self._handle.fetch(self._cell_data)
         self._output = Mesh(pts, cells, cd)

@@ -27,6 +27,7 @@ class Image:
     origin: tuple = (0.0, 0.0, 0.0)
     direction: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
     meta: dict = field(default_factory=dict)
+    region_index: tuple = (0, 0, 0)   # itk::ImageRegion::GetIndex of the buffered region (x, y, z)
 
 
 def read_mha(path: str) -> Image:

@@ -59,6 +59,8 @@ struct orc_params {
   uint32_t max_steps;
   uint32_t image_border_faces;  // 0: the reference (clamped neighbours: no face on the image border);
                                 // 1: a neighbour outside the image is outside the surface (closed mesh, txx:133 TODO)
+  int64_t region_index[3];      // image index of the buffer's first voxel (ImageRegion::GetIndex; the tests of the
+                                // reference only have 0): TransformIndexToPhysicalPoint sees index + region_index
 };
 
 struct orc_mesh {
@@ -81,6 +83,7 @@ struct Geometry {
   int64_t nx, ny, nz;
   double spacing[3];
   double origin[3];
+  int64_t i0[3];  // image index of buffer voxel (0, 0, 0)
 };
 
 template <typename T>
@@ -133,7 +136,7 @@ inline InterpSetup interp_setup(const Geometry& g, const double p[3]) {
   cont_index(g, p, ci);
   for (int a = 0; a < 3; ++a) {
     const double f = std::floor(ci[a]);
-    s.base[a] = (int64_t)f;
+    s.base[a] = (int64_t)f - g.i0[a];  // buffer-relative (the continuous index is an IMAGE index)
     s.dist[a] = ci[a] - f;
   }
   return s;
@@ -251,7 +254,7 @@ inline void project_vertex(const Volume<T>& v, const orc_params& P, double step0
 inline void corner_position(const Geometry& g, int64_t cx, int64_t cy, int64_t cz, float out[3]) {
   const int64_t idx[3] = {cx, cy, cz};
   for (int a = 0; a < 3; ++a) {
-    float p = (float)(g.spacing[a] * (double)idx[a] + g.origin[a]);  // TransformIndexToPhysicalPoint -> Point<float>
+    float p = (float)(g.spacing[a] * (double)(idx[a] + g.i0[a]) + g.origin[a]);  // TransformIndexToPhysicalPoint -> Point<float>
     p = (float)((double)p - g.spacing[a] / 2.0);                     // vertex[a] -= spacing[a]/2.0
     out[a] = p;
   }
@@ -482,8 +485,9 @@ void sample_typed(const void* data, const Geometry& g, const double* pts, uint64
   }
 }
 
-Geometry make_geometry(const uint64_t dims[3], const double spacing[3], const double origin[3]) {
+Geometry make_geometry(const uint64_t dims[3], const double spacing[3], const double origin[3], const int64_t* i0 = nullptr) {
   Geometry g;
+  for (int a = 0; a < 3; ++a) g.i0[a] = i0 ? i0[a] : 0;
   g.nx = (int64_t)dims[0]; g.ny = (int64_t)dims[1]; g.nz = (int64_t)dims[2];
   for (int a = 0; a < 3; ++a) { g.spacing[a] = spacing ? spacing[a] : 1.0; g.origin[a] = origin ? origin[a] : 0.0; }
   return g;
@@ -508,7 +512,7 @@ extern "C" {
 
 orc_mesh* orc_cuberille(const void* data, int dtype, const uint64_t dims[3], const double spacing[3],
                         const double origin[3], const orc_params* P) {
-  const Geometry g = make_geometry(dims, spacing, origin);
+  const Geometry g = make_geometry(dims, spacing, origin, P->region_index);
   orc_mesh* m = nullptr;
   ORC_DISPATCH(dtype, m = run_typed<T>(data, g, *P));
   return m;
@@ -539,7 +543,7 @@ int orc_classify(const void* data, int dtype, const uint64_t dims[3], double iso
 // ProjectVertexToIsoSurface on caller points, in place.
 int orc_project_points(const void* data, int dtype, const uint64_t dims[3], const double spacing[3],
                        const double origin[3], const orc_params* P, float* pts, uint64_t n) {
-  const Geometry g = make_geometry(dims, spacing, origin);
+  const Geometry g = make_geometry(dims, spacing, origin, P->region_index);
   ORC_DISPATCH(dtype, project_typed<T>(data, g, *P, pts, n));
   return 0;
 }

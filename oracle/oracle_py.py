@@ -37,6 +37,7 @@ class _Params(C.Structure):
         ("step_relaxation", C.c_double),
         ("max_steps", C.c_uint32),
         ("image_border_faces", C.c_uint32),
+        ("region_index", C.c_int64 * 3),
     ]
 
 
@@ -98,17 +99,20 @@ def _geom(vol: np.ndarray, spacing, origin):
     return dims, sp, og
 
 
-def _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces=False) -> _Params:
+def _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces=False,
+            region_index=(0, 0, 0)) -> _Params:
     return _Params(float(iso), int(bool(triangles)), int(bool(project)), int(bool(cell_data)), int(mode),
-                   float(thr), float(step), float(relax), int(max_steps), int(bool(border_faces)))
+                   float(thr), float(step), float(relax), int(max_steps), int(bool(border_faces)),
+                   (C.c_int64 * 3)(*[int(v) for v in region_index]))
 
 
 def cuberille(vol: np.ndarray, iso, *, triangles=True, project=True, cell_data=False, mode=LITERAL,
-              thr=0.5, step=-1.0, relax=0.95, max_steps=50, spacing=None, origin=None, border_faces=False) -> Mesh:
+              thr=0.5, step=-1.0, relax=0.95, max_steps=50, spacing=None, origin=None, border_faces=False,
+              region_index=(0, 0, 0)) -> Mesh:
     """Run the oracle.  `vol` is indexed [z, y, x] (x fastest), like a MetaImage buffer."""
     L = lib()
     dims, sp, og = _geom(vol, spacing, origin)
-    P = _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces)
+    P = _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces, region_index)
     h = L.orc_cuberille(vol.ctypes.data, DTYPE_CODES[vol.dtype], dims, sp, og, C.byref(P))
     if not h:
         raise RuntimeError("oracle: unsupported dtype")

@@ -124,6 +124,24 @@ def test_image_border_faces_with_projection_slabs_and_raster_order():
     assert_mesh_equal(P.Mesh(np.concatenate(pts), np.concatenate(cells)), ref, "border faces + slabs")
 
 
+@pytest.mark.parametrize("tri,proj,border", [(False, False, False), (True, True, False), (True, True, True)])
+def test_buffered_region_with_a_nonzero_index(tri, proj, border):
+    """the buffer's first voxel has image index (4, -3, 10): points are TransformIndexToPhysicalPoint(index + that),
+    the interpolators work with image indices (oracle flag region_index)"""
+    P, O = pkg(), oracle()
+    vol = gyroid((20, 18, 22), 9.0, border=False if border else -2.0)
+    geo = dict(spacing=(0.7, 1.1, 1.9), origin=(1.5, -2.25, 3.0))
+    ref = O.cuberille(vol, 0.0, triangles=tri, project=proj, thr=0.01, mode=O.CLOSED_FORM, border_faces=border,
+                      region_index=(4, -3, 10), **geo)
+    img = P.Image(vol, geo["spacing"], geo["origin"])
+    img.region_index = (4, -3, 10)
+    mesh = run_filter(img, 0.0, triangles=tri, project=proj, thr=0.01, border_faces=border)
+    assert_mesh_equal(mesh, ref, "region index")
+    # and it is not a no-op
+    ref0 = O.cuberille(vol, 0.0, triangles=tri, project=proj, thr=0.01, mode=O.CLOSED_FORM, border_faces=border, **geo)
+    assert not np.array_equal(ref0.points, ref.points)
+
+
 def test_assign_by_second_sweep_gives_the_same_mesh(monkeypatch):
     """CUB_ASSIGN_SWEEP=1: K3a recomputes the ownership masks in a second sweep instead of reading the ones K2a
     stored (32 B of scratch per lattice entry less)"""
