@@ -129,7 +129,9 @@ int cub_set_region_index(cub_handle h, const int64_t index[3]);
  * image (2 slices below: one for face/corner classification, one so that the
  * first-touch owner of a shared corner is computed identically on both sides;
  * 1 slice above for the +z faces; more is harmless);
- * with projection the halo should be >= 8 slices (vertex travel).  Default
+ * with projection the halo must cover the travel of a vertex, up to
+ * step_length / (1 - step_relaxation) = 5 x the largest spacing by default, i.e.
+ * >= 8 slices for isotropic voxels and more when the z spacing is the small one.  Default
  * (never called): the buffer is the whole image.                               */
 int cub_set_slab(cub_handle h, uint64_t image_nz, uint64_t local_z0,
                  uint64_t own_z0, uint64_t own_z1);

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
         const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
         A[k] = __ldg(a.act + e);
         C[k] = __ldg(a.cofs + e);
-        if (lane == 31) Cn[k] = __ldg(a.cofs + e + 1u);
+        if (lane == 31 || w == g.Wx - 1) Cn[k] = __ldg(a.cofs + e + 1u);  // (the next lane has no voxel word: it loads nothing)
       }
       fbase = __ldg(a.fofs + e00);
       c0 = __ldg(row);
@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const uint32_t nx = __shfl_down_sync(0xffffffffu, C[k], 1);
-      if (lane != 31) Cn[k] = nx;
+      if (lane != 31 && w != g.Wx - 1) Cn[k] = nx;
     }
     if (valid) {
       const uint32_t XB = g.X & 31;

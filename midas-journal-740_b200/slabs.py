@@ -23,7 +23,8 @@ class Slab:
 
 def plan_slabs(image_nz: int, world: int, halo: int = 2) -> list[Slab]:
     """Contiguous, near-equal z-slabs; `halo` >= 2 (classification + first-touch ownership of the shared
-    corner plane); use >= 8 when vertices are projected (they travel up to step/(1-relax) voxels)."""
+    corner plane); when vertices are projected they travel up to step / (1 - relax) = 5 x the largest spacing by
+    default: use >= 8 for isotropic voxels, and 5 * max(spacing) / spacing_z + 3 in general."""
     if halo < 2:
         raise ValueError("the halo must be at least 2 slices")
     if world < 1 or image_nz < world:

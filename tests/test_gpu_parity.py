@@ -54,7 +54,9 @@ def test_bitmask_matches_oracle(dtype, shape):
 
 @pytest.mark.parametrize("dtype", [np.uint8, np.int16, np.uint16, np.float32, np.float64, np.int32])
 @pytest.mark.parametrize("shape,fill", [((6, 7, 8), 0.5), ((9, 33, 65), 0.5), ((17, 20, 97), 0.2), ((12, 40, 200), 0.8),
-                                        ((2, 3, 4), 0.5), ((1, 1, 1), 0.5), ((3, 3, 1), 0.5), ((1, 5, 40), 0.5)])
+                                        ((2, 3, 4), 0.5), ((1, 1, 1), 0.5), ((3, 3, 1), 0.5), ((1, 5, 40), 0.5),
+                                        # rows that end on a word boundary: the corner column x = X starts a corner word
+                                        ((5, 6, 32), 0.5), ((24, 8, 96), 0.7), ((4, 9, 64), 0.3)])
 def test_noise_volumes_ids_and_connectivity(dtype, shape, fill):
     """iid noise exercises every corner configuration of the first-touch rule, with inside voxels on
     the image border (no faces there); quads and fixed-split triangles, unprojected: exact positions"""
