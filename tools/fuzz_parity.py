@@ -1,5 +1,6 @@
 """Randomised parity run: random shapes, pixel types, fills and option combinations, CUDA path against the oracle
-(bit-exact).  Usage: python tools/fuzz_parity.py [seconds] [seed]"""
+(bit-exact).  Usage: python tools/fuzz_parity.py [seconds] [seed] [big]   (big: long rows / many rows: several
+sweep tiles, several 32-word segments per row, several packed-classify tasks per row)"""
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -8,12 +9,16 @@ from util import assert_mesh_equal, assert_mesh_equal_up_to_vertex_order, oracle
 
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 seed = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+big = len(sys.argv) > 3
 rng = np.random.default_rng(seed)
 P, O = pkg(), oracle()
 dtypes = [np.uint8, np.int8, np.uint16, np.int16, np.uint32, np.int32, np.float32, np.float64]
 t0, n = time.time(), 0
 while time.time() - t0 < budget:
-    shape = (int(rng.integers(1, 28)), int(rng.integers(1, 36)), int(rng.choice([1, 2, 31, 32, 33, 64, 65, 96, 128, 130, 192, 256])) if rng.random() < 0.5 else int(rng.integers(1, 140)))
+    if big:
+        shape = (int(rng.integers(1, 10)), int(rng.integers(1, 70)), int(rng.choice([512, 544, 1024, 1056, 1152, 2048, 2080])) if rng.random() < 0.5 else int(rng.integers(300, 2300)))
+    else:
+      shape = (int(rng.integers(1, 28)), int(rng.integers(1, 36)), int(rng.choice([1, 2, 31, 32, 33, 64, 65, 96, 128, 130, 192, 256])) if rng.random() < 0.5 else int(rng.integers(1, 140)))
     dt = dtypes[int(rng.integers(len(dtypes)))]
     smooth = rng.random() < 0.4 and min(shape) >= 4 and dt not in (np.int8,)
     if smooth:
