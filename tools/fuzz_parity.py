@@ -69,6 +69,7 @@ while time.time() - t0 < budget:
                 assert_mesh_equal(m2, ref, what + f" slabs {cuts}")
     except Exception:
         print("FAILED:", what, flush=True)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         np.save(os.path.join(ROOT, "gpurun_out", "fuzz_fail.npy"), vol)
         for t2 in (False, True):
             for c2 in (False, True):
