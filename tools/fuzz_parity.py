@@ -27,9 +27,10 @@ while time.time() - t0 < budget:
         vol, iso = random_volume(shape, dt, seed=int(rng.integers(1 << 30)), fill=float(rng.choice([0.05, 0.3, 0.5, 0.7, 0.95])))
     tri, proj = bool(rng.integers(2)), bool(rng.integers(2)) and smooth
     cd, border, raster = bool(rng.integers(2)), bool(rng.integers(2)), rng.random() < 0.25
+    idb = 8 if rng.random() < 0.3 else 4
     geo = dict(spacing=tuple(float(x) for x in rng.choice([0.5, 1.0, 1.25, 2.0], 3)), origin=tuple(float(x) for x in rng.integers(-5, 6, 3)))
     ridx = tuple(int(x) for x in rng.integers(-4, 5, 3)) if rng.random() < 0.3 else (0, 0, 0)
-    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ridx={ridx} {geo}"
+    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} {geo}"
     kw = dict(triangles=tri, project=proj, cell_data=cd, thr=0.02)
     ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, border_faces=border, region_index=ridx, **kw, **geo)
     img = P.Image(vol, geo["spacing"], geo["origin"]); img.region_index = ridx
@@ -44,7 +45,7 @@ while time.time() - t0 < budget:
             else:
                 assert mesh.points.shape[0] == 0 and mesh.cells.shape[0] == 0
         else:
-            mesh = run_filter(img, iso, border_faces=border, **kw)
+            mesh = run_filter(img, iso, border_faces=border, id_bytes=idb, **kw)
             assert_mesh_equal(mesh, ref, what)
             # the same through z-slabs
             nz = shape[0]
@@ -61,7 +62,10 @@ while time.time() - t0 < budget:
                     lo, hi = max(0, z0 - halo), min(nz, z1 + halo)
                     h = P.capi.Handle(0)
                     h.set_volume(vol[lo:hi], geo["spacing"], geo["origin"]); h.set_region_index(ridx); h.set_slab(nz, lo, z0, z1)
-                    a, b = h.count(prm); h.set_id_base(pb, cb); h.emit(4)
+                    a, b = h.count(prm)
+                    if rng.random() < 0.5:
+                        h.emit_vertices()
+                    h.set_id_base(pb, cb); h.emit(idb)
                     x, y, z = h.fetch(cd)
                     pts.append(x); cells.append(y); cds.append(z)
                     pb += a; cb += b * (2 if tri else 1); h.close()
