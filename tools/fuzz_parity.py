@@ -71,6 +71,31 @@ while time.time() - t0 < budget:
                     pb += a; cb += b * (2 if tri else 1); h.close()
                 m2 = P.Mesh(np.concatenate(pts), np.concatenate(cells), np.concatenate(cds) if cd else None)
                 assert_mesh_equal(m2, ref, what + f" slabs {cuts}")
+            # the same through slabs.run_streamed (host volume in, host mesh out, several handles / streams)
+            if nz >= 4 and not cd and rng.random() < 0.2:
+                import torch
+                n_sl, n_h, resident = int(rng.integers(2, min(nz, 6) + 1)), int(rng.integers(2, 4)), bool(rng.integers(2))
+                vt = torch.from_numpy(vol).pin_memory()
+                vpc = 3 if tri else 4
+                pts_h = torch.zeros((ref.points.shape[0] + 4, 3), dtype=torch.float32).pin_memory()
+                cells_h = torch.zeros((ref.cells.shape[0] + 4, vpc), dtype=torch.int32).pin_memory()
+                prm = P.capi.default_params()
+                prm.iso_value, prm.generate_triangles, prm.project_vertices = float(iso), int(tri), int(proj)
+                prm.image_border_faces, prm.surface_distance_threshold = int(border), 0.02
+                kw2 = {}
+                if resident:
+                    sts = [torch.cuda.Stream() for _ in range(n_h)]
+                    hs = [P.capi.Handle(0, st.cuda_stream) for st in sts]
+                    kw2 = dict(device_volume=torch.empty(vol.nbytes, dtype=torch.uint8, device="cuda"), streams=sts)
+                else:
+                    hs = [P.capi.Handle(0) for _ in range(n_h)]
+                if ridx == (0, 0, 0):  # (run_streamed has no region index parameter)
+                    a, b = P.slabs.run_streamed(hs, vt.data_ptr(), vol.dtype, (shape[2], shape[1], shape[0]), prm, n_sl, pts_h.data_ptr(),
+                                                cells_h.data_ptr(), halo=nz if proj else 2, spacing=geo["spacing"], origin=geo["origin"], **kw2)
+                    assert (a, b) == (ref.points.shape[0], ref.cells.shape[0]), what + " streamed counts"
+                    assert_mesh_equal(P.Mesh(pts_h.numpy()[:a], cells_h.numpy()[:b].view(np.uint32)), ref, what + f" streamed {n_sl}/{n_h}/{resident}")
+                for h in hs:
+                    h.close()
     except Exception:
         print("FAILED:", what, flush=True)
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
