@@ -96,7 +96,7 @@ __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx,
   }
 }
 
-constexpr int kFaceThreads = 256;
+constexpr int kFaceThreads = 128;
 
 // per-word context a warp shares through shared memory: 5 x uint4
 //   [0] A[oz][oy]   active masks of the 4 corner words       [1] C[oz][oy]  their slot bases
@@ -110,11 +110,13 @@ struct FaceSmem {
 // compacted into a queue and handled one per lane, so a word with ten surface voxels does not stall the 31
 // lanes whose words have none.
 template <typename IdT, int MODE, bool CD>
-__global__ void __launch_bounds__(kFaceThreads, 6) k_faces(const FaceArgs a) {
+__global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // grid: x = 32-word segments of a row, y = groups of 8 rows (one row per warp), z = own slices
+  // grid: x = 32-word segments of a row, y = groups of 4 rows (one row per warp), z = own slices.  128-thread CTAs:
+  // a CTA keeps its registers and shared memory until its last warp is done, and warps differ a lot here (r1: 256
+  // threads 1.127 ms of emission, 128 threads 1.084, 64 threads 1.121)
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kFaceThreads / 32) + warp, zl = a.z_begin + blockIdx.z;
 
   // ---- face masks of the word (txx:164-173; clamped neighbours: no face on the image border) --------------
