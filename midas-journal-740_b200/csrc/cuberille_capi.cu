@@ -659,8 +659,9 @@ static int emit_vertex_stage(cub_handle h) {
       a.cnt = h->cnt.p; a.vofs = h->vofs.p; a.own = h->own.p;
       a.X = g.X; a.Y = g.Y; a.Wx = g.Wx; a.EY = h->EY; a.EW = h->EW; a.z_begin = h->owner_z_min;
       a.vtx = h->vtx.p;
-      const dim3 grid((g.Wx + 31) / 32, (g.Y + 7) / 8, h->zs1 - h->owner_z_min);
-      k_assign<<<grid, 256, 0, h->stream>>>(a);
+      const int rows = kAssignThreads / 32;
+      const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, h->zs1 - h->owner_z_min);
+      k_assign<<<grid, kAssignThreads, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     } else {

@@ -22,9 +22,11 @@ struct AssignArgs {
   uint32_t* vtx;          // [n vertices] cx | cy << 16 | oz << 31
 };
 
-__global__ void __launch_bounds__(256) k_assign(const AssignArgs a) {
-  // grid: x = 32-word segments of a row, y = groups of 8 rows (one row per warp), z = slices of the scan range
-  const int w = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
+constexpr int kAssignThreads = 128;  // (one row per warp)
+
+__global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
+  // grid: x = 32-word segments of a row, y = groups of kAssignThreads / 32 rows (one row per warp), z = slices of the scan range
+  const int w = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
   if (w >= a.Wx || y >= a.Y) return;
   const uint32_t e = ((uint32_t)z * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;
   if ((__ldg(a.cnt + e) & 0x3ffu) == 0) return;
