@@ -45,7 +45,7 @@ __device__ __constant__ const int8_t kFaceCorners[6][4] = {{0, 4, 7, 3}, {0, 1, 
 
 // unprojected vertex position, AddVertex txx:265-270 (ITK 3.x form):
 //   p = (float)(spacing*index + origin);  p = (float)((double)p - spacing/2)
-__device__ __forceinline__ float corner_coord(double spacing, double origin, long long idx) {
+__device__ __forceinline__ float corner_coord(double spacing, double origin, int idx) {
   float p = (float)__dadd_rn(__dmul_rn(spacing, (double)idx), origin);
   return (float)__dadd_rn((double)p, -(spacing / 2.0));
 }

@@ -476,7 +476,7 @@ int cub_set_region_index(cub_handle h, const int64_t index[3]) {
   if (!h->has_volume) return fail(h, CUB_ERR_INVALID, "cub_set_region_index before cub_set_volume");
   for (int k = 0; k < 3; ++k) {
     const long long v = index ? (long long)index[k] : 0;
-    if (v < -(1ll << 40) || v > (1ll << 40)) return fail(h, CUB_ERR_INVALID, "region index out of range");
+    if (v < -(1ll << 30) || v > (1ll << 30)) return fail(h, CUB_ERR_INVALID, "region index beyond +-2^30 is not supported");
     h->i0[k] = v;
   }
   h->counted = h->emitted = false;
@@ -688,7 +688,7 @@ static int emit_vertex_stage(cub_handle h) {
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
       a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
-      a.coff[0] = h->i0[0] - h->pad; a.coff[1] = h->i0[1] - h->pad; a.coff[2] = h->i0[2] + g.zg0 - h->pad;
+      a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
       a.points = h->points.p; a.perm = h->perm.p;
       k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
       h->launches++;
@@ -699,7 +699,7 @@ static int emit_vertex_stage(cub_handle h) {
     RasterPointArgs a{};
     a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
     a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
-    a.coff[0] = h->i0[0] - h->pad; a.coff[1] = h->i0[1] - h->pad; a.coff[2] = h->i0[2] + g.zg0 - h->pad;
+    a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
     a.geom = h->geom; a.points = h->points.p;
     const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
     k_points_raster<<<grid, 256, 0, h->stream>>>(a);

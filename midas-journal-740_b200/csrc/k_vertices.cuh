@@ -27,7 +27,7 @@ struct VertexArgs {
   const uint32_t* cofs;
   int EY, EW;
   int plane_lo, plane_hi;   // local corner planes that faces of this handle reference (inclusive)
-  long long coff[3];        // image index of lattice corner (0, 0, 0): slab offset, region index, minus the pad of image_border_faces
+  int coff[3];              // image index of lattice corner (0, 0, 0): slab offset, region index, minus the pad of image_border_faces
   Geom geom;
   float* points;            // indexed by scan-relative vertex id
   uint32_t* perm;           // [active corners of planes plane_lo..plane_hi] -> scan-relative vertex id
@@ -115,7 +115,7 @@ struct RasterPointArgs {
   const uint32_t* cofs;
   int EY, EW, Wc;
   int plane_lo, plane_hi;   // local corner planes to emit (inclusive)
-  long long coff[3];        // as in VertexArgs
+  int coff[3];              // as in VertexArgs
   Geom geom;
   float* points;            // indexed by slot
 };
