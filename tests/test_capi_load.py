@@ -73,3 +73,23 @@ def test_filter_mirror_defaults_and_clamps():
     assert isinstance(f.GetInterpolator(), P.LinearInterpolateImageFunction)
     with pytest.raises(TypeError):
         f.SetInterpolator(object())
+
+
+def test_params_struct_layout_matches_the_header(tmp_path):
+    """the ctypes mirror of cub_params (capi.Params) has the layout the C compiler gives the header's struct"""
+    import ctypes as C
+    import os
+    import subprocess
+    P = pkg()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "layout.c"
+    fields = [name for name, _ in P.capi.Params._fields_]
+    body = "\n".join(f'  printf("{f} %zu\\n", offsetof(cub_params, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cuberille_c.h"\nint main(void) {\n'
+                   '  printf("sizeof %zu\\n", sizeof(cub_params));\n' + body + "\n  return 0;\n}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)])
+    out = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    assert int(out["sizeof"]) == C.sizeof(P.capi.Params)
+    for f in fields:
+        assert int(out[f]) == getattr(P.capi.Params, f).offset, f

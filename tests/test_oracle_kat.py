@@ -140,3 +140,18 @@ def test_image_border_faces_close_the_mesh():
     a = O.cuberille(vol, 128, triangles=True, project=False, mode=O.CLOSED_FORM, border_faces=True)
     b = O.cuberille(padded, 128, triangles=True, project=False, mode=O.CLOSED_FORM, origin=(-1.0, -1.0, -1.0))
     assert np.array_equal(a.cells, b.cells) and np.array_equal(a.points, b.points)
+
+
+def test_oracle_params_struct_layout():
+    """oracle_py._Params mirrors orc_params field for field (a drift would silently change what the oracle computes)"""
+    import ctypes as C
+    import os
+    import re
+    O = oracle()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "oracle", "cuberille_oracle.cpp")).read()
+    body = text[text.index("struct orc_params {"):]
+    body = body[:body.index("};")]
+    names = re.findall(r"^\s*(?:double|int32_t|uint32_t|int64_t)\s+(\w+)", body, re.M)
+    assert names == [n for n, _ in O._Params._fields_]
+    assert C.sizeof(O._Params) == 8 + 4 * 4 + 3 * 8 + 2 * 4 + 3 * 8
