@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CUB_ABI_VERSION 1
+#define CUB_ABI_VERSION 2
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -142,8 +142,18 @@ int cub_set_slab(cub_handle h, uint64_t image_nz, uint64_t local_z0,
  * (n_cells of the final mesh is n_quads, or 2*n_quads with triangles.)         */
 int cub_count(cub_handle h, const cub_params *p, uint64_t *n_points, uint64_t *n_quads);
 
+/* Slices of halo a z-slab needs below / above its own range for these parameters:
+ * 2 / 1 without projection; with projection the reach of a vertex (the geometric
+ * sum of its <= max_steps + 2 moves, txx:464-469) plus the interpolation and
+ * central-difference footprints.  cub_count refuses a slab whose buffer is
+ * shorter (a clamped read would silently change the mesh).                     */
+int cub_projection_halo(const cub_params *p, const double spacing[3],
+                        uint64_t *below, uint64_t *above);
+
 /* Global id bases for z-slab runs: the exclusive scan over ranks of the
- * (n_points, n_cells) returned by cub_count.  Default 0, 0.                    */
+ * (n_points, n_cells) returned by cub_count.  Default 0, 0.  The bases live on
+ * the device (the emission kernels read them there); this call queues the
+ * update on the handle's stream.                                               */
 int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base);
 
 /* Optional early half of cub_emit: queues the vertex stage (vertex creation
@@ -166,6 +176,30 @@ int cub_emit(cub_handle h, int id_bytes);
  * n_cells counts final cells (triangles when generate_triangles).              */
 int cub_run(cub_handle h, const cub_params *p, int id_bytes,
             uint64_t *n_points, uint64_t *n_cells);
+
+/* The same two phases WITHOUT a host round trip in between.  The counts stay in
+ * device memory, where the emission kernels (and the multi-GPU count exchange,
+ * cub_comm_exchange_counts) read them; nothing blocks the calling thread until
+ * cub_finish.  cub_emit_async writes into the result buffers the handle already
+ * has (they only grow: the first run of a handle sizes them through one
+ * synchronisation); should a later run produce more than they hold, the kernels
+ * stop at the end of the buffers and cub_finish redoes the emission with larger
+ * ones - the caller never sees a truncated mesh.
+ *   cub_count_async  : queues phase 1
+ *   cub_device_counts: device pointer to {n_points, n_quads} of the own range
+ *   cub_emit_async   : queues phase 2
+ *   cub_finish       : synchronises, returns the counts, validates the emission
+ * cub_fetch / cub_device_buffers call cub_finish themselves when needed.       */
+int cub_count_async(cub_handle h, const cub_params *p);
+int cub_device_counts(cub_handle h, const uint64_t **counts);
+int cub_emit_async(cub_handle h, int id_bytes);
+int cub_finish(cub_handle h, uint64_t *n_points, uint64_t *n_cells);
+
+/* Non-fatal remark about the last count (never NULL, "" if none).  Currently:
+ * an empty voxel slice between occupied ones, where the reference's lookup-plane
+ * rotation (txx:155-161, it only advances on inside voxels) merges vertices of
+ * different corner planes and this library does not.   */
+const char *cub_last_warning(cub_handle h);
 
 /* Copies the mesh out: what mesh->GetPoints()->InsertElement (txx:275) and
  * mesh->SetCell (txx:313,320,329) received, in the reference's id order.
@@ -190,6 +224,44 @@ int cub_synchronize(cub_handle h);
 int cub_device_buffers(cub_handle h, const float **points, const void **cells,
                        const void **cell_data, uint64_t *n_points, uint64_t *n_cells,
                        int *verts_per_cell, int *id_bytes);
+
+/* ---- multi-GPU: z-slabs over NCCL -----------------------
+ * No counterpart in the reference (GenerateData is one raster loop on one core,
+ * txx:136-206).  One handle per GPU, each with its slab (cub_set_slab); a
+ * communicator binds the handle to its rank.  NCCL is loaded at run time
+ * (libnccl.so.2), single-GPU users do not need it.
+ *   cub_comm_unique_id      : ncclGetUniqueId (rank 0; the host distributes the 128 bytes)
+ *   cub_comm_create         : ncclCommInitRank on the handle's device (collective)
+ *   cub_comm_exchange_counts: after cub_count / cub_count_async.  All-gather of the
+ *                             (points, quads) of every rank's own range, device to
+ *                             device on a side stream; the exclusive prefix becomes
+ *                             the handle's id bases (what cub_set_id_base would set).
+ *                             Nothing blocks the host: cub_emit(_async) orders its
+ *                             face kernel after the exchange by itself.
+ *   cub_comm_counts         : the gathered counts on the host, 2 * world values
+ *                             (points, quads per rank); synchronises the exchange
+ *   cub_comm_gather_mesh    : "allgatherv" over NVLink: every rank receives the whole
+ *                             mesh into DEVICE buffers sized for the totals (points:
+ *                             3 floats each; cells: verts_per_cell ids of id_bytes;
+ *                             cell_data: pixels), each rank's part at its id base -
+ *                             the concatenation IS the single-GPU mesh.  Queued on the
+ *                             handle's stream (cub_synchronize to wait).  Any buffer
+ *                             may be NULL on ALL ranks alike.                         */
+typedef struct cub_comm_s *cub_comm;
+int cub_comm_unique_id(unsigned char id[128]);
+int cub_comm_create(cub_handle h, const unsigned char id[128], int world, int rank, cub_comm *out);
+int cub_comm_destroy(cub_comm c);
+int cub_comm_exchange_counts(cub_comm c);
+int cub_comm_counts(cub_comm c, uint64_t *counts);
+int cub_comm_gather_mesh(cub_comm c, float *points, void *cells, void *cell_data);
+
+/* Device memory for hosts that do not link the CUDA runtime themselves (the
+ * destination buffers of cub_comm_gather_mesh, CUB_MEM_DEVICE volumes):
+ * cudaMalloc / cudaFree / a blocking copy (kinds: CUB_MEM_*) on the handle's
+ * device and stream.                                                           */
+int cub_device_alloc(cub_handle h, uint64_t bytes, void **out);
+int cub_device_free(cub_handle h, void *p);
+int cub_device_copy(cub_handle h, void *dst, const void *src, uint64_t bytes, int dst_kind, int src_kind);
 
 /* Diagnostics for parity tests of the individual kernels.
  * cub_debug_bitmask: the 1-bit/voxel inside mask of the local buffer after

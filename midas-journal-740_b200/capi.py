@@ -30,6 +30,9 @@ SYMBOLS = [
     "cub_synchronize", "cub_device_buffers",
     "cub_debug_bitmask", "cub_debug_project_points", "cub_generate_volume", "cub_download_volume",
     "cub_enable_timing", "cub_get_timings", "cub_launch_count",
+    "cub_projection_halo", "cub_count_async", "cub_device_counts", "cub_emit_async", "cub_finish", "cub_last_warning",
+    "cub_comm_unique_id", "cub_comm_create", "cub_comm_destroy", "cub_comm_exchange_counts", "cub_comm_counts",
+    "cub_comm_gather_mesh", "cub_device_alloc", "cub_device_free", "cub_device_copy",
 ]
 
 
@@ -118,8 +121,47 @@ def load() -> C.CDLL:
     L.cub_get_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.cub_launch_count.restype = u64
     L.cub_launch_count.argtypes = [vp]
+    L.cub_projection_halo.restype = i
+    L.cub_projection_halo.argtypes = [C.POINTER(Params), pd, pu64, pu64]
+    L.cub_count_async.restype = i
+    L.cub_count_async.argtypes = [vp, C.POINTER(Params)]
+    L.cub_device_counts.restype = i
+    L.cub_device_counts.argtypes = [vp, C.POINTER(vp)]
+    L.cub_emit_async.restype = i
+    L.cub_emit_async.argtypes = [vp, i]
+    L.cub_finish.restype = i
+    L.cub_finish.argtypes = [vp, pu64, pu64]
+    L.cub_last_warning.restype = C.c_char_p
+    L.cub_last_warning.argtypes = [vp]
+    L.cub_device_alloc.restype = i
+    L.cub_device_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.cub_device_free.restype = i
+    L.cub_device_free.argtypes = [vp, vp]
+    L.cub_device_copy.restype = i
+    L.cub_device_copy.argtypes = [vp, vp, vp, u64, i, i]
+    L.cub_comm_unique_id.restype = i
+    L.cub_comm_unique_id.argtypes = [vp]
+    L.cub_comm_create.restype = i
+    L.cub_comm_create.argtypes = [vp, vp, i, i, C.POINTER(vp)]
+    L.cub_comm_destroy.restype = i
+    L.cub_comm_destroy.argtypes = [vp]
+    L.cub_comm_exchange_counts.restype = i
+    L.cub_comm_exchange_counts.argtypes = [vp]
+    L.cub_comm_counts.restype = i
+    L.cub_comm_counts.argtypes = [vp, pu64]
+    L.cub_comm_gather_mesh.restype = i
+    L.cub_comm_gather_mesh.argtypes = [vp, vp, vp, vp]
     _lib = L
     return L
+
+
+def projection_halo(params: Params, spacing=(1.0, 1.0, 1.0)) -> tuple[int, int]:
+    """Halo slices (below, above) a z-slab needs for these parameters (cub_projection_halo)."""
+    lo, hi = C.c_uint64(), C.c_uint64()
+    rc = load().cub_projection_halo(C.byref(params), (C.c_double * 3)(*spacing), C.byref(lo), C.byref(hi))
+    if rc != 0:
+        raise CuberilleError(rc, "cub_projection_halo")
+    return lo.value, hi.value
 
 
 def default_params() -> Params:
@@ -204,6 +246,27 @@ class Handle:
         self._check(self._L.cub_count(self._h, C.byref(params), C.byref(npts), C.byref(nq)))
         return npts.value, nq.value
 
+    def count_async(self, params: Params):
+        """Queue phase 1 without waiting for the counts (they stay on the device)."""
+        self._check(self._L.cub_count_async(self._h, C.byref(params)))
+
+    def emit_async(self, id_bytes: int = 4):
+        self._check(self._L.cub_emit_async(self._h, id_bytes))
+
+    def finish(self):
+        """Synchronise; returns (n_points, n_cells) of the queued run."""
+        npts, nc = C.c_uint64(), C.c_uint64()
+        self._check(self._L.cub_finish(self._h, C.byref(npts), C.byref(nc)))
+        return npts.value, nc.value
+
+    def device_counts_ptr(self) -> int:
+        p = C.c_void_p()
+        self._check(self._L.cub_device_counts(self._h, C.byref(p)))
+        return p.value
+
+    def last_warning(self) -> str:
+        return self._L.cub_last_warning(self._h).decode()
+
     def set_id_base(self, point_base: int, cell_base: int):
         self._check(self._L.cub_set_id_base(self._h, point_base, cell_base))
 
@@ -271,3 +334,42 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._L.cub_launch_count(self._h))
+
+
+def comm_unique_id() -> bytes:
+    """ncclGetUniqueId through the C-ABI (rank 0 calls it, the host distributes the 128 bytes)."""
+    buf = (C.c_ubyte * 128)()
+    rc = load().cub_comm_unique_id(buf)
+    if rc != 0:
+        raise CuberilleError(rc, "cub_comm_unique_id failed (is libnccl.so.2 loadable?)")
+    return bytes(buf)
+
+
+class Comm:
+    """One cub_comm: binds a Handle to its rank of an NCCL communicator created by the library."""
+
+    def __init__(self, handle: Handle, unique_id: bytes, world: int, rank: int):
+        self._L, self._handle = handle._L, handle
+        self._c = C.c_void_p()
+        self.world, self.rank = world, rank
+        buf = (C.c_ubyte * 128).from_buffer_copy(unique_id)
+        handle._check(self._L.cub_comm_create(handle._h, buf, world, rank, C.byref(self._c)))
+
+    def close(self):
+        if self._c:
+            self._L.cub_comm_destroy(self._c)
+            self._c = C.c_void_p()
+
+    def exchange_counts(self):
+        """Queue the all-gather of the counts + the device-side prefix that becomes the id bases."""
+        self._handle._check(self._L.cub_comm_exchange_counts(self._c))
+
+    def counts(self) -> list[tuple[int, int]]:
+        out = (C.c_uint64 * (2 * self.world))()
+        self._handle._check(self._L.cub_comm_counts(self._c, out))
+        return [(int(out[2 * r]), int(out[2 * r + 1])) for r in range(self.world)]
+
+    def gather_mesh(self, points_ptr: int, cells_ptr: int, cell_data_ptr: int = 0):
+        self._handle._check(self._L.cub_comm_gather_mesh(self._c, C.c_void_p(points_ptr) if points_ptr else None,
+                                                         C.c_void_p(cells_ptr) if cells_ptr else None,
+                                                         C.c_void_p(cell_data_ptr) if cell_data_ptr else None))

@@ -1,4 +1,4 @@
-// cub_common.cuh — shared device-side definitions of libcuberille_cuda.so (sm_100a).
+// cbr_common.cuh — shared device-side definitions of libcuberille_cuda.so (sm_100a).
 //
 // Data layout in HBM:
 //   volume   : [Zl][Y][X] pixels, x fastest (the itk::Image buffer, or a z-slab of it)
@@ -22,7 +22,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-namespace cub {
+namespace cbr {
 
 struct Grid {
   int X, Y, Zl;  // local buffer size in voxels
@@ -43,16 +43,36 @@ __host__ __device__ constexpr int corner_oz(int l) { return (l >= 4) ? 1 : 0; }
 __device__ __constant__ const int8_t kFaceCorners[6][4] = {{0, 4, 7, 3}, {0, 1, 5, 4}, {1, 2, 6, 5},
                                                            {2, 3, 7, 6}, {0, 3, 2, 1}, {4, 5, 6, 7}};
 
-// unprojected vertex position, AddVertex txx:265-270 (ITK 3.x form):
-//   p = (float)(spacing*index + origin);  p = (float)((double)p - spacing/2)
-__device__ __forceinline__ float corner_coord(double spacing, double origin, int idx) {
-  float p = (float)__dadd_rn(__dmul_rn(spacing, (double)idx), origin);
-  return (float)__dadd_rn((double)p, -(spacing / 2.0));
-}
-
 struct Geom {
   double spacing[3];
   double origin[3];
+  // oriented images (a non-identity direction matrix): index -> physical matrix M = direction * diag(spacing)
+  // and its inverse, both row-major; unused (and the ITK 3.x expressions are evaluated) when oriented == 0
+  double m[9];
+  double minv[9];
+  int oriented;
 };
 
-}  // namespace cub
+// unprojected vertex position, AddVertex txx:265-270:
+//   TransformIndexToPhysicalPoint:  identity direction (every test of the reference), the ITK 3.x form
+//                                       p = (float)(spacing*index + origin)
+//                                   oriented image, the ITK 4/5 form (the point is a Point<float>, so every
+//                                   accumulation rounds to float)
+//                                       p = (float)origin;  for j: p = (float)((double)p + M[a][j]*index[j])
+//   then, on every PHYSICAL axis (the reference does not rotate the shift, txx:268-270):
+//                                       p = (float)((double)p - spacing/2)
+__device__ __forceinline__ float corner_coord(const Geom& g, int a, int ix, int iy, int iz) {
+  float p;
+  if (!g.oriented) {
+    const int idx = a == 0 ? ix : (a == 1 ? iy : iz);
+    p = (float)__dadd_rn(__dmul_rn(g.spacing[a], (double)idx), g.origin[a]);
+  } else {
+    p = (float)g.origin[a];
+    p = (float)__dadd_rn((double)p, __dmul_rn(g.m[3 * a + 0], (double)ix));
+    p = (float)__dadd_rn((double)p, __dmul_rn(g.m[3 * a + 1], (double)iy));
+    p = (float)__dadd_rn((double)p, __dmul_rn(g.m[3 * a + 2], (double)iz));
+  }
+  return (float)__dadd_rn((double)p, -(g.spacing[a] / 2.0));
+}
+
+}  // namespace cbr

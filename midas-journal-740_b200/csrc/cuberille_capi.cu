@@ -1,9 +1,11 @@
 // cuberille_capi.cu — the C-ABI of include/cuberille_c.h: handle, buffers, kernel launches.
 //
 // Host-side orchestration of GenerateData() (txx:59-216) as a two-phase run:
-//   cub_count : K1 classify -> K2 count + decoupled look-back scan      (sizes are data dependent)
-//   cub_emit  : K3 emit points + cells -> [K4 project] -> [K5 split projected quads]
-// Everything is ordered on one CUDA stream.  There is no CPU implementation behind this file.
+//   cub_count : K1 classify -> K2a ownership sweep -> K2b segment scan (decoupled look-back)   (sizes are data dependent)
+//   cub_emit  : K3a vertices (points + corner -> id map) -> K3c faces -> [K4 project] -> [K5 split projected quads]
+// Everything is ordered on one CUDA stream.  The counts of a run live in a small device-side info block that the
+// emission kernels read themselves, so a whole step can also be queued without a host round trip
+// (cub_count_async / cub_emit_async / cub_finish).  There is no CPU implementation behind this file.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -14,61 +16,67 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/cuberille_c.h"
-#include "cub_common.cuh"
+#include "cbr_common.cuh"
 #include "k_classify.cuh"
-#include "k_count_scan.cuh"
+#include "k_segscan.cuh"
 #include "k_generate.cuh"
 #include "k_faces.cuh"
 #include "k_project.cuh"
 #include "k_sweep.cuh"
-#include "k_assign.cuh"
 #include "k_vertices.cuh"
 
-using namespace cub;
+using namespace cbr;
 
 namespace {
 
-// SMs of the device the handles run on (148 on a B200; refreshed by cub_create): grid sizes are multiples of it
-int kNumSMs = 148;
+// tuning knobs, read from the environment ONCE per handle (cub_create) and clamped to sane values
+struct Knobs {
+  int count_cfg = -1;        // CUB_COUNT_CFG: sweep tile configuration (-1: by row length)
+  int k1_packed = 1;         // CUB_K1_PACKED: 4-bytes-per-lane classify for 8/16-bit pixels
+  int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
+  int proj_ctas = 5;         // CUB_PROJ_CTAS_PER_SM
+};
+
+int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* v = getenv(name);
+  if (!v || !*v) return dflt;
+  const int x = atoi(v);
+  return x < lo ? lo : (x > hi ? hi : x);
+}
 
 // slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
-int pick_tz(int gx, int gy, int nz) {
+int pick_tz(int gx, int gy, int nz, int num_sms) {
   int tz = 32;
-  while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * kNumSMs) tz >>= 1;
+  while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * num_sms) tz >>= 1;
   if (tz > nz) tz = nz;
   return tz < 1 ? 1 : tz;
 }
 
 // One instantiation of the sweep kernel (thread grid NTX x NTY, R corner rows per thread; k_sweep.cuh)
 template <typename C>
-cudaError_t launch_sweep(SweepArgs a, cudaStream_t stream) {
+cudaError_t launch_sweep(SweepArgs a, cudaStream_t stream, int num_sms) {
   using Smem = SweepSmem<C>;
   auto kern = k_sweep<C>;
   const int gx = (a.g.Wx + C::TXW - 1) / C::TXW, gy = (a.g.Y + C::TY - 1) / C::TY;
   const int nz = a.z_end - a.z_begin;
-  a.tz = pick_tz(gx, gy, nz);
+  a.tz = pick_tz(gx, gy, nz, num_sms);
   dim3 grid(gx, gy, (nz + a.tz - 1) / a.tz);
   kern<<<grid, C::NTP, sizeof(Smem), stream>>>(a);
   return cudaGetLastError();
 }
 
-int tuning_knob(const char* name, int dflt) {
-  const char* v = getenv(name);
-  return v ? atoi(v) : dflt;
-}
-
-template <int MODE>
-cudaError_t dispatch_sweep(const SweepArgs& a, cudaStream_t st) {
+cudaError_t dispatch_sweep(const SweepArgs& a, cudaStream_t st, int num_sms, int cfg_knob) {
   // wide tiles (16 voxel words per row) for big volumes, narrow ones (8) when a row has few words
-  const int cfg = tuning_knob(MODE == MODE_COUNT ? "CUB_COUNT_CFG" : "CUB_ASSIGN_CFG", a.g.Wx > 8 ? 2 : 10);
+  const int cfg = cfg_knob >= 0 ? cfg_knob : (a.g.Wx > 8 ? 2 : 10);
   switch (cfg) {
-    case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE>>(a, st);
-    case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE>>(a, st);
-    case 2: return launch_sweep<SweepCfg<17, 7, 2, MODE>>(a, st);
-    case 3: return launch_sweep<SweepCfg<17, 7, 4, MODE>>(a, st);
-    default: return launch_sweep<SweepCfg<9, 14, 2, MODE>>(a, st);
+    case 0: return launch_sweep<SweepCfg<17, 15, 1, MODE_COUNT>>(a, st, num_sms);
+    case 1: return launch_sweep<SweepCfg<17, 15, 2, MODE_COUNT>>(a, st, num_sms);
+    case 2: return launch_sweep<SweepCfg<17, 7, 2, MODE_COUNT>>(a, st, num_sms);
+    case 3: return launch_sweep<SweepCfg<17, 7, 4, MODE_COUNT>>(a, st, num_sms);
+    default: return launch_sweep<SweepCfg<9, 14, 2, MODE_COUNT>>(a, st, num_sms);
   }
 }
 
@@ -82,9 +90,12 @@ struct DevBuf {
 
 struct cub_handle_s {
   int device = 0;
+  int num_sms = 148;           // SMs of the handle's device: grid sizes are multiples of it
+  Knobs knobs;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::string err = "";
+  std::string warning = "";
 
   // volume
   const void* d_vol = nullptr;
@@ -95,21 +106,20 @@ struct cub_handle_s {
   bool has_volume = false;
   // slab
   uint64_t image_nz = 0, local_z0 = 0, own_z0 = 0, own_z1 = 0;
+  bool slab_set = false;
 
   // scratch
-  DevBuf<uint32_t> bits, cnt, act, vofs, fofs, cofs, perm;
+  DevBuf<uint32_t> bits, cnt, act, perm, slice_any;
   DevBuf<uint4> own;         // K2a -> K3a: the 8 ownership masks per voxel word (2 x uint4 per entry)
-  DevBuf<uint32_t> vtx;
-  DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
-  uint64_t ent_layout[3] = {0, 0, 0};
-  int EY = 0, EW = 0;
-  uint64_t n_active = 0, ghost_c = 0;   // active corners of the scanned planes / of the bottom plane (slab below owns them)
+  DevBuf<uint4> seg;         // K2b -> K3: segment bases {vertices, faces, active corners, -}
+  int EY = 0, EW = 0, NS = 0;
+  uint64_t n_active = 0;     // active corners of the counted planes (size of the corner -> id map)
   bool raster = false;
   uint64_t bits_layout[3] = {0, 0, 0};
-  DevBuf<unsigned long long> status;  // 2 * n_tiles
+  DevBuf<unsigned long long> status;  // 3 * n_tiles
   unsigned int* d_ticket = nullptr;
-  unsigned long long* d_totals = nullptr;  // 6
-  unsigned long long* h_totals = nullptr;  // pinned, 6
+  unsigned long long* d_info = nullptr;  // kInfoWords (k_segscan.cuh) + 2 work counters
+  unsigned long long* h_info = nullptr;  // pinned copy
 
   // results
   DevBuf<float> points;
@@ -122,12 +132,17 @@ struct cub_handle_s {
   Grid gv{};   // the voxel buffer itself (K1, K4, cell data)
   long long i0[3] = {0, 0, 0};  // image index of buffer voxel (0, 0, 0): cub_set_region_index
   int pad = 0, zpad_lo = 0;  // image_border_faces: lattice (x, y, z) is voxel (x - pad, y - pad, z - zpad_lo)
-  bool counted = false, emitted = false;
+  bool count_queued = false;    // the count kernels of the current run are on the stream
+  bool counted = false;         // ... and the host knows their results
+  bool emitted = false;
+  bool emit_unverified = false; // the emission was queued with buffer sizes that the host has not checked yet (cub_emit_async)
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
-  bool own_valid = false;       // K2a stored the ownership masks of the current count
   bool vertices_done = false;   // the vertex stage of the current count has been queued (cub_emit_vertices)
+  bool projected = false;       // the points of the current count have been projected in place
   uint64_t n_points = 0, n_quads = 0, n_cells = 0, ghost_v = 0, ghost_f = 0;
   uint64_t point_base = 0, cell_base = 0;
+  uint64_t flags = 0;
+  cudaEvent_t wait_before_faces = nullptr;  // set by a queued count exchange (cuberille_comm.inl): the id bases are valid after it
   int id_bytes = 4, verts_per_cell = 4;
   double step_used = 0.0;
 
@@ -245,7 +260,7 @@ struct ClassifyPacked<T, true> {
   static bool launch(cub_handle h, const T* vol, uint32_t* bits, const Grid& g, unsigned long long rows,
                      unsigned long long max_blocks, cudaStream_t stream) {
     constexpr int vpl = 4 / (int)sizeof(T);
-    if (g.X % (32 * vpl) != 0 || (reinterpret_cast<uintptr_t>(vol) & 3u) != 0 || tuning_knob("CUB_K1_PACKED", 1) == 0) return false;
+    if (g.X % (32 * vpl) != 0 || (reinterpret_cast<uintptr_t>(vol) & 3u) != 0 || h->knobs.k1_packed == 0) return false;
     const unsigned tasks_per_row = (unsigned)((g.Wx + 31) / 32);
     const unsigned long long tasks = rows * tasks_per_row;  // cub_count checks rows * groups < 2^32
     unsigned long long blocks = std::min<unsigned long long>((tasks + 7) / 8, max_blocks);
@@ -257,7 +272,7 @@ struct ClassifyPacked<T, true> {
 
 template <typename T>
 void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas_per_sm) {
-  const unsigned long long max_blocks = (unsigned long long)kNumSMs * ctas_per_sm;
+  const unsigned long long max_blocks = (unsigned long long)h->num_sms * ctas_per_sm;
   h->launches++;
   if (h->pad) {
     // the padded lattice (image_border_faces): z0 / z1 are lattice slices
@@ -290,7 +305,9 @@ void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas
     k_classify<T, false><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
 }
 
-int launch_project(cub_handle h, float* pts, size_t n) {
+// K4 on `pts` (explicit count n), or - from_info - on the handle's point buffer with the range taken from the
+// device-side run info (n = the capacity of the buffer)
+int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool include_ghost) {
   if (n == 0) return CUB_OK;
   ProjArgs a;
   a.vol = h->d_vol;
@@ -304,10 +321,12 @@ int launch_project(cub_handle h, float* pts, size_t n) {
   a.max_steps = h->params.max_steps;
   a.points = pts;
   a.n_points = n;
-  a.work = h->d_totals + 7;
+  a.info = from_info ? h->d_info : nullptr;
+  a.include_ghost = include_ghost ? 1 : 0;
+  a.work = h->d_info + kInfoWords;
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
-  const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)kNumSMs * tuning_knob("CUB_PROJ_CTAS_PER_SM", 5));
+  const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)h->num_sms * h->knobs.proj_ctas);
   DISPATCH_PIXEL(h->dtype, (k_project<T><<<blocks, 128, 0, h->stream>>>(a)));
   h->launches++;
   CU_TRY(h, cudaGetLastError());
@@ -391,11 +410,16 @@ int cub_create(int device, void* stream, cub_handle* out) {
   }
   {
     int sms = 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) kNumSMs = sms;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) h->num_sms = sms;
+    // the tuning knobs are read here, once, and clamped (a zero would make a launch with no blocks)
+    h->knobs.count_cfg = env_int("CUB_COUNT_CFG", -1, -1, 10);
+    h->knobs.k1_packed = env_int("CUB_K1_PACKED", 1, 0, 1);
+    h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
+    h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
   }
   bool ok = cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
-            cudaMalloc(&h->d_totals, 8 * sizeof(unsigned long long)) == cudaSuccess &&
-            cudaMallocHost(&h->h_totals, 8 * sizeof(unsigned long long)) == cudaSuccess;
+            cudaMalloc(&h->d_info, (kInfoWords + 2) * sizeof(unsigned long long)) == cudaSuccess &&
+            cudaMallocHost(&h->h_info, (kInfoWords + 2) * sizeof(unsigned long long)) == cudaSuccess;
   for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
   cub_default_params(&h->params);
@@ -408,9 +432,10 @@ int cub_destroy(cub_handle h) {
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
-  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->cofs.p); cudaFree(h->perm.p); cudaFree(h->vtx.p); cudaFree(h->own.p); cudaFree(h->vsl.p); cudaFree(h->vofs.p); cudaFree(h->fofs.p); cudaFree(h->status.p);
-  cudaFree(h->d_ticket); cudaFree(h->d_totals);
-  if (h->h_totals) cudaFreeHost(h->h_totals);
+  cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->perm.p); cudaFree(h->own.p); cudaFree(h->seg.p);
+  cudaFree(h->slice_any.p); cudaFree(h->status.p);
+  cudaFree(h->d_ticket); cudaFree(h->d_info);
+  if (h->h_info) cudaFreeHost(h->h_info);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
   for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->own_stream) cudaStreamDestroy(h->stream);
@@ -446,7 +471,7 @@ static int set_geometry(cub_handle h, int dtype, const uint64_t dims[3], const d
   h->local_z0 = 0;
   h->own_z0 = 0;
   h->own_z1 = dims[2];
-  h->counted = h->emitted = false;
+  h->counted = h->emitted = h->count_queued = false;
   return CUB_OK;
 }
 
@@ -479,7 +504,7 @@ int cub_set_region_index(cub_handle h, const int64_t index[3]) {
     if (v < -(1ll << 30) || v > (1ll << 30)) return fail(h, CUB_ERR_INVALID, "region index beyond +-2^30 is not supported");
     h->i0[k] = v;
   }
-  h->counted = h->emitted = false;
+  h->counted = h->emitted = h->count_queued = false;
   return CUB_OK;
 }
 
@@ -500,25 +525,70 @@ int cub_set_slab(cub_handle h, uint64_t image_nz, uint64_t local_z0, uint64_t ow
   h->local_z0 = local_z0;
   h->own_z0 = own_z0;
   h->own_z1 = own_z1;
-  h->counted = h->emitted = false;
+  h->slab_set = true;
+  h->counted = h->emitted = h->count_queued = false;
   return CUB_OK;
 }
 
-int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n_quads) {
-  if (!h) return CUB_ERR_INVALID;
+}  // extern "C"
+
+namespace {
+
+// slices a projected vertex can reach below / above the plane it starts on: the travel is at most the geometric sum of
+// the step lengths (max_steps + 2 moves, txx:464-469), trilinear interpolation reads one node further and the central
+// differences one more (SURVEY section 7 "projection halo")
+void projection_reach(const cub_params& P, double step_used, double spacing_z, uint64_t* below, uint64_t* above) {
+  const double r = P.step_relaxation, n = (double)P.max_steps + 2.0;
+  double travel = (r >= 1.0) ? step_used * n : step_used * (1.0 - std::pow(r, n)) / (1.0 - r);
+  if (!(travel >= 0.0)) travel = 0.0;
+  const double t = std::ceil(travel / spacing_z - 1e-9);
+  const uint64_t ct = t > 1e9 ? (uint64_t)1e9 : (uint64_t)t;
+  *below = ct + 3;  // (the ghost vertices of the plane under the own range are projected too, for the triangle split)
+  *above = ct + 2;
+}
+
+// ---- the count phase, queued on the handle's stream (no host synchronisation) ----------------------------------
+int count_launch(cub_handle h, const cub_params* p) {
   if (!p) return fail(h, CUB_ERR_INVALID, "params is null");
   CU_TRY(h, cudaSetDevice(h->device));
-  h->counted = h->emitted = false;
+  h->counted = h->emitted = h->count_queued = h->emit_unverified = false;
+  h->wait_before_faces = nullptr;
   h->params = *p;
   CUB_TRY(setup_grid(h));
   if (iso_as_pixel(h->dtype, p->iso_value) != p->iso_value)
     return fail(h, CUB_ERR_INVALID, "iso value %.17g is not representable in the pixel type", p->iso_value);
   compute_step(h);
   const Grid& g = h->g;
+  // the halo contract (cub_set_slab checks it too; cub_generate_volume with a z offset does not go through it)
+  {
+    const uint64_t zl = h->dims[2];
+    const uint64_t need_lo = h->own_z0 >= 2 ? h->own_z0 - 2 : 0;
+    const uint64_t need_hi = h->own_z1 + 1 < h->image_nz ? h->own_z1 + 1 : h->image_nz;
+    if (!(h->own_z0 < h->own_z1) || h->own_z1 > h->image_nz || h->local_z0 > need_lo || h->local_z0 + zl < need_hi ||
+        h->owner_z_min < 0 || h->zs1 > g.Zl)
+      return fail(h, CUB_ERR_INVALID, "the local buffer [%llu,%llu) does not cover the own range [%llu,%llu) plus its halo: call cub_set_slab",
+                  (unsigned long long)h->local_z0, (unsigned long long)(h->local_z0 + zl), (unsigned long long)h->own_z0,
+                  (unsigned long long)h->own_z1);
+    if (p->project_vertices && (h->local_z0 > 0 || h->local_z0 + zl < h->image_nz)) {
+      // a true slab: the projection must not run into the end of the local buffer (its reads would be clamped there
+      // and the result would differ from the whole-image run without any error)
+      uint64_t below = 0, above = 0;
+      projection_reach(*p, h->step_used, h->geom.spacing[2], &below, &above);
+      const uint64_t lo = h->own_z0 > below ? h->own_z0 - below : 0;
+      const uint64_t hi = h->own_z1 + above < h->image_nz ? h->own_z1 + above : h->image_nz;
+      if (h->local_z0 > lo || h->local_z0 + zl < hi)
+        return fail(h, CUB_ERR_INVALID,
+                    "projection needs a halo of %llu slices below and %llu above the own range (cub_projection_halo): the local "
+                    "buffer must cover [%llu,%llu)", (unsigned long long)below, (unsigned long long)above,
+                    (unsigned long long)lo, (unsigned long long)hi);
+    }
+  }
   if ((unsigned long long)g.Y * g.Zl * ((g.Wx + kWordsPerTask - 1) / kWordsPerTask) >= (1ull << 32))
     return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
   if ((unsigned long long)g.Y * g.Wp >= (1ull << 31)) return fail(h, CUB_ERR_UNSUPPORTED, "x*y too large");
   if (g.X > 65534 || g.Y > 32766) return fail(h, CUB_ERR_UNSUPPORTED, "x size above 65534 or y size above 32766 voxels is not supported");
+  if (h->zs1 + 1 - h->owner_z_min > 65535)
+    return fail(h, CUB_ERR_UNSUPPORTED, "more than 65534 slices in one handle: split into z-slabs");
   const size_t words = (size_t)g.Zl * g.Y * g.Wp;
   const bool layout_changed = h->bits_layout[0] != (uint64_t)g.X || h->bits_layout[1] != (uint64_t)g.Y ||
                               h->bits_layout[2] != (uint64_t)g.Zl;
@@ -526,41 +596,45 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
   CUB_TRY(ensure(h, h->bits, words));
   if ((!had || layout_changed) && g.Wp != g.Wx) CU_TRY(h, cudaMemsetAsync(h->bits.p, 0, words * 4, h->stream));
   h->bits_layout[0] = g.X; h->bits_layout[1] = g.Y; h->bits_layout[2] = g.Zl;
-  // entry lattice of the counts / offsets / active masks: one entry per corner word, (Zl+1) x (Y+1) x EW
+  // entry lattice of the counts / active masks: one entry per corner word, (Zl+1) x (Y+1) x EW; NS segments of 32 per row
   const int Wc = (g.X + 32) / 32;
   h->EY = g.Y + 1;
   h->EW = (Wc + 1 + 3) & ~3;
+  h->NS = (h->EW + 31) / 32;
   const size_t plane_entries = (size_t)h->EY * h->EW;
   const size_t entries = plane_entries * (size_t)(g.Zl + 1);
-  if (entries + kScanTile >= (1ull << 32)) return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
-  const bool had_e = h->cnt.p && h->cnt.cap >= entries;
+  const size_t lattice_rows = (size_t)h->EY * (size_t)(g.Zl + 1);
+  if (entries + 4096 >= (1ull << 32)) return fail(h, CUB_ERR_INVALID, "volume too large for one handle: split into z-slabs");
+  const bool had_e = h->cnt.p && h->cnt.cap >= entries && h->act.p && h->act.cap >= entries + 4;
   CUB_TRY(ensure(h, h->cnt, entries));
   CUB_TRY(ensure(h, h->act, entries + 4));
-  CUB_TRY(ensure(h, h->vofs, entries));
-  CUB_TRY(ensure(h, h->fofs, entries));
-  CUB_TRY(ensure(h, h->cofs, entries + 4));
-  const bool keep_own = p->vertex_order != CUB_ORDER_RASTER && tuning_knob("CUB_ASSIGN_SWEEP", 0) == 0;
-  if (keep_own) CUB_TRY(ensure(h, h->own, 2 * entries));
-  // entries that K2a never writes (padding columns) must read as zero counts
-  if (!had_e || layout_changed) CU_TRY(h, cudaMemsetAsync(h->cnt.p, 0, entries * 4, h->stream));
+  CUB_TRY(ensure(h, h->seg, lattice_rows * h->NS));
+  CUB_TRY(ensure(h, h->slice_any, (size_t)g.Zl + 1));
+  h->raster = p->vertex_order == CUB_ORDER_RASTER;
+  if (!h->raster) CUB_TRY(ensure(h, h->own, 2 * entries));
+  // entries that K2a never writes (padding columns) must read as zero counts / empty masks
+  if (!had_e || layout_changed) {
+    CU_TRY(h, cudaMemsetAsync(h->cnt.p, 0, entries * 4, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->act.p, 0, (entries + 4) * 4, h->stream));
+  }
 
   if (h->timing) cudaEventRecord(h->ev[2], h->stream);
 
   // K2 scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
-  const size_t e_begin = (size_t)h->owner_z_min * plane_entries;
-  const size_t n_scan = (size_t)(h->zs1 + 1 - h->owner_z_min) * plane_entries;
-  // one large scan tile per resident CTA (4 CTAs/SM), so that every tile is in flight when the look-backs run
+  const size_t row_begin = (size_t)h->owner_z_min * h->EY;
+  const size_t n_rows = (size_t)(h->zs1 + 1 - h->owner_z_min) * h->EY;
+  // one large scan tile per resident CTA, so that every tile is in flight when the look-backs run
   int scan_occ = 0;
-  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_count_scan, kScanThreads, 0));
-  const size_t max_tiles = (size_t)kNumSMs * std::max(1, std::min(scan_occ, tuning_knob("CUB_SCAN_CTAS_PER_SM", 8)));
-  size_t scan_tile = ((n_scan + max_tiles - 1) / max_tiles + kScanTile - 1) / kScanTile * kScanTile;
-  if (scan_tile < (size_t)kScanTile) scan_tile = kScanTile;
-  const size_t n_tiles = (n_scan + scan_tile - 1) / scan_tile;
+  CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_seg_scan, kScanThreads, 0));
+  const size_t max_tiles = (size_t)h->num_sms * std::max(1, std::min(scan_occ, h->knobs.scan_ctas));
+  size_t rows_per_tile = ((n_rows + max_tiles - 1) / max_tiles + kScanWarps - 1) / kScanWarps * kScanWarps;
+  if (rows_per_tile < (size_t)kScanWarps) rows_per_tile = kScanWarps;
+  const size_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
   CUB_TRY(ensure(h, h->status, 3 * n_tiles));
   SweepArgs ca{};
   ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
-  ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = keep_own ? h->own.p : nullptr;
-  h->own_valid = keep_own;
+  ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = h->raster ? nullptr : h->own.p;
+  ca.slice_any = h->slice_any.p;
   {
     // K1 then K2a on the handle's stream.  (Running the HBM-bound K1 beside the issue-bound K2a, on two streams by
     // z-chunks or even without any dependency, was measured in r1 and took K1 + K2a: DESIGN.md section 8.)
@@ -570,27 +644,32 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
       CU_TRY(h, cudaGetLastError());
       t.stop();
     }
+    CU_TRY(h, cudaMemsetAsync(h->slice_any.p, 0, ((size_t)g.Zl + 1) * 4, h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->d_info, 0, (kInfoWords + 2) * sizeof(unsigned long long), h->stream));
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
     ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
-    CU_TRY(h, dispatch_sweep<MODE_COUNT>(ca, h->stream));
+    CU_TRY(h, dispatch_sweep(ca, h->stream, h->num_sms, h->knobs.count_cfg));
     h->launches++;
   }
   {
-    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
     if (h->timing) cudaEventRecord(h->ev[6], h->stream);
-    ScanArgs sa{};
-    sa.cnt = h->cnt.p; sa.vofs = h->vofs.p; sa.fofs = h->fofs.p; sa.cofs = h->cofs.p;
-    sa.e_begin = e_begin; sa.n = n_scan;
-    sa.plane_entries = (unsigned)plane_entries; sa.plane_lo = (unsigned)h->zs0;
-    sa.status = h->status.p; sa.n_tiles = (unsigned)n_tiles; sa.tile = scan_tile; sa.ticket = h->d_ticket; sa.totals = h->d_totals;
-    k_count_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
+    SegScanArgs sa{};
+    sa.cnt = h->cnt.p; sa.seg = h->seg.p;
+    sa.row_begin = (unsigned)row_begin; sa.n_rows = (unsigned)n_rows;
+    sa.EW = (unsigned)h->EW; sa.NS = (unsigned)h->NS;
+    sa.ghost_row_end = (unsigned)((size_t)h->zs0 * h->EY);
+    // the prefixes at the first own entry: what the ghost slice below contributed (slab runs)
+    sa.mark_row_vf = (h->owner_z_min < h->zs0) ? (unsigned)((size_t)h->zs0 * h->EY) : 0xffffffffu;
+    // raster order: the corners of the bottom plane of a slab's range belong to the slab underneath
+    sa.mark_row_c = (h->own_z0 > 0) ? (unsigned)((size_t)(h->zs0 + 1) * h->EY) : 0xffffffffu;
+    sa.rows_per_tile = (unsigned)rows_per_tile; sa.n_tiles = (unsigned)n_tiles;
+    sa.status = h->status.p; sa.ticket = h->d_ticket; sa.info = h->d_info;
+    k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
-    const size_t mark0 = (h->owner_z_min < h->zs0) ? (size_t)h->zs0 * plane_entries : (size_t)-1;
-    // raster order: the corners of the bottom plane of a slab's range belong to the slab underneath
-    const size_t mark_c = (h->own_z0 > 0) ? (size_t)(h->zs0 + 1) * plane_entries : (size_t)-1;
-    k_gather_marks<<<1, 32, 0, h->stream>>>(h->vofs.p, h->fofs.p, h->cofs.p, mark0, mark_c, h->d_totals);
+    k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->slice_any.p, h->owner_z_min, h->zs1);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     if (h->timing) {
@@ -600,107 +679,95 @@ int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n
       cudaEventElapsedTime(&h->ms[7], h->ev[6], h->ev[1]);  // the scan alone
     }
   }
-  CU_TRY(h, cudaMemcpyAsync(h->h_totals, h->d_totals, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
+  h->point_base = h->cell_base = 0;
+  h->count_queued = true;
+  h->vertices_done = false;
+  h->projected = false;
+  return CUB_OK;
+}
+
+// ---- the host learns the counts: one device -> host copy and one synchronisation -----------------------------------
+int count_finish(cub_handle h) {
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (h->wait_before_faces) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->wait_before_faces, 0));
+  CU_TRY(h, cudaMemcpyAsync(h->h_info, h->d_info, kInfoWords * sizeof(unsigned long long), cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   if (h->timing) {
     cudaEventRecord(h->ev[3], h->stream);
     cudaEventSynchronize(h->ev[3]);
     cudaEventElapsedTime(&h->ms[5], h->ev[2], h->ev[3]);
   }
-  const uint64_t tot_v = h->h_totals[0], tot_f = h->h_totals[1];
+  const uint64_t tot_v = h->h_info[kInfoTotV], tot_f = h->h_info[kInfoTotF];
   if (tot_v >= (1ull << 32) || tot_f >= (1ull << 32))
     return fail(h, CUB_ERR_OVERFLOW, "more than 2^32 vertices or faces in one handle (%llu, %llu): split into z-slabs",
                 (unsigned long long)tot_v, (unsigned long long)tot_f);
-  h->n_active = h->h_totals[2];
-  h->ghost_f = h->h_totals[4];
-  h->ghost_c = h->h_totals[5];
-  h->raster = p->vertex_order == CUB_ORDER_RASTER;
+  h->n_active = h->h_info[kInfoTotC];
+  h->ghost_f = h->h_info[kInfoMarkF];
   // scan-relative vertex ids below ghost_v belong to the slab underneath (first-touch order: what the ghost
   // slice created; raster order: the corners of the shared bottom plane)
-  h->ghost_v = h->raster ? h->ghost_c : h->h_totals[3];
-  h->n_points = (h->raster ? h->n_active : tot_v) - h->ghost_v;
-  h->n_quads = tot_f - h->ghost_f;
-  h->point_base = h->cell_base = 0;
+  h->ghost_v = h->h_info[kInfoGhostV];
+  h->n_points = h->h_info[kInfoPoints];
+  h->n_quads = h->h_info[kInfoQuads];
+  h->point_base = h->h_info[kInfoPointBase];
+  h->cell_base = h->h_info[kInfoCellBase];
+  h->flags = h->h_info[kInfoFlags];
+  h->warning.clear();
+  if (h->flags & kFlagEmptyInteriorSlice)
+    h->warning = "an empty voxel slice lies between occupied slices: the reference filter merges vertices of different corner "
+                 "planes there (its lookup-plane rotation only advances on inside voxels, txx:155-161); this mesh follows the "
+                 "intended rule and may differ from the reference's";
   h->counted = true;
-  h->vertices_done = false;
-  if (n_points) *n_points = h->n_points;
-  if (n_quads) *n_quads = h->n_quads;
   return CUB_OK;
 }
 
-int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base) {
-  if (!h) return CUB_ERR_INVALID;
-  h->point_base = point_id_base;
-  h->cell_base = cell_id_base;
-  return CUB_OK;
-}
+// The vertex stage of cub_emit: K3a (reference order) or k_points_raster.  It needs the counts but not the id
+// base, so a multi-GPU caller can queue it before the ranks have exchanged their counts (cub_emit_vertices).
+// exact: the host knows the counts and sizes the buffers; otherwise the buffers keep their sizes (the kernels
+// guard their writes and flag an overflow).
+const int kNeedSizes = -1000;
 
-// The vertex stage of cub_emit: K3a + K3b (reference order) or k_points_raster.  It needs the counts but not the
-// id base, so a multi-GPU caller can queue it before the ranks have exchanged their counts (cub_emit_vertices).
-static int emit_vertex_stage(cub_handle h) {
+int emit_vertex_stage(cub_handle h, bool exact) {
   const cub_params& P = h->params;
   const Grid& g = h->g;
   const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0;
   const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
-  const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
-  CUB_TRY(ensure(h, h->points, 3 * n_pts_all));
-  if (!h->raster) {
-    CUB_TRY(ensure(h, h->vtx, n_pts_all));
-    CUB_TRY(ensure(h, h->vsl, (size_t)(h->zs1 - h->owner_z_min) + 1 + (n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds));
-    CUB_TRY(ensure(h, h->perm, (size_t)h->n_active));
+  if (exact) {
+    const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
+    CUB_TRY(ensure(h, h->points, 3 * (n_pts_all + n_pts_all / 16)));
+    if (!h->raster) CUB_TRY(ensure(h, h->perm, (size_t)h->n_active + (size_t)h->n_active / 16));
+    if (h->n_quads == 0) { h->vertices_done = true; return CUB_OK; }
+  } else if (!h->points.p || (!h->raster && !h->perm.p)) {
+    return kNeedSizes;
   }
   h->vertices_done = true;
-  if (h->n_quads == 0) return CUB_OK;
-  const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
+  h->projected = false;
+  // the points of the vertices the slab underneath owns are only needed by the projected triangle split
+  const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
   if (!h->raster) {
-    if (h->own_valid) {
-      // K3a: vertex id -> lattice corner, walking the ownership masks K2a stored (reference creation order)
-      AssignArgs a{};
-      a.cnt = h->cnt.p; a.vofs = h->vofs.p; a.own = h->own.p;
-      a.X = g.X; a.Y = g.Y; a.Wx = g.Wx; a.EY = h->EY; a.EW = h->EW; a.z_begin = h->owner_z_min;
-      a.vtx = h->vtx.p;
-      const int rows = kAssignThreads / 32;
-      const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, h->zs1 - h->owner_z_min);
-      k_assign<<<grid, kAssignThreads, 0, h->stream>>>(a);
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
-    } else {
-      // K3a, first version: a second z-sweep that recomputes the ownership masks (CUB_ASSIGN_SWEEP=1)
-      SweepArgs a{};
-      a.bits = h->bits.p; a.g = g; a.Wc = (g.X + 32) / 32; a.EY = h->EY; a.EW = h->EW;
-      a.z_begin = h->owner_z_min; a.z_end = h->zs1;
-      a.vofs = h->vofs.p; a.vtx = h->vtx.p;
-      CU_TRY(h, dispatch_sweep<MODE_ASSIGN>(a, h->stream));
-      h->launches++;
-    }
-    {
-      // K3b: points + corner -> id map
-      const int nz = h->zs1 - h->owner_z_min;
-      const unsigned n_blocks = (unsigned)((n_pts_all + kVertexBlockIds - 1) / kVertexBlockIds);
-      SliceIndexArgs si{};
-      si.vofs = h->vofs.p; si.plane_entries = (size_t)h->EY * h->EW; si.z_first = h->owner_z_min; si.nz = nz;
-      si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
-      const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
-      k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
-      h->launches++;
-      VertexArgs a{};
-      a.vtx = h->vtx.p; a.n = n_pts_all; a.first_point = ghost_points ? 0 : (size_t)h->ghost_v;
-      a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
-      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
-      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
-      a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
-      a.points = h->points.p; a.perm = h->perm.p;
-      k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
-    }
+    VertexArgs a{};
+    a.cnt = h->cnt.p; a.act = h->act.p; a.own = h->own.p; a.seg = h->seg.p; a.info = h->d_info;
+    a.Wx = g.Wx; a.Y = g.Y; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS;
+    a.z_begin = h->owner_z_min;
+    a.plane_lo = h->zs0; a.plane_hi = h->zs1;
+    a.write_ghost_points = ghost_points ? 1 : 0;
+    a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
+    a.geom = h->geom;
+    a.points = h->points.p; a.points_cap = h->points.cap / 3;
+    a.perm = h->perm.p; a.perm_cap = h->perm.cap;
+    a.flags = h->d_info + kInfoFlags;
+    const int rows = kVertexThreads / 32;
+    const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, h->zs1 - h->owner_z_min);
+    k_vertices<<<grid, kVertexThreads, 0, h->stream>>>(a);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
   } else {
     // raster order: vertex id = corner slot, points straight from the active masks
     RasterPointArgs a{};
-    a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW; a.Wc = (g.X + 32) / 32;
+    a.act = h->act.p; a.seg = h->seg.p; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.Wc = (g.X + 32) / 32;
     a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
     a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
-    a.geom = h->geom; a.points = h->points.p;
+    a.geom = h->geom; a.points = h->points.p; a.points_cap = h->points.cap / 3;
+    a.flags = h->d_info + kInfoFlags;
     const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
     k_points_raster<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
@@ -709,49 +776,51 @@ static int emit_vertex_stage(cub_handle h) {
   return CUB_OK;
 }
 
-int cub_emit_vertices(cub_handle h) {
-  if (!h) return CUB_ERR_INVALID;
-  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_emit_vertices before cub_count");
-  CU_TRY(h, cudaSetDevice(h->device));
-  if (h->vertices_done || h->timing) return CUB_OK;  // (per-kernel timing keeps the whole emission inside cub_emit)
-  return emit_vertex_stage(h);
-}
-
-int cub_emit(cub_handle h, int id_bytes) {
-  if (!h) return CUB_ERR_INVALID;
-  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_emit before cub_count");
-  if (id_bytes != 4 && id_bytes != 8) return fail(h, CUB_ERR_INVALID, "id_bytes must be 4 or 8");
+int emit_launch(cub_handle h, int id_bytes, bool exact) {
   CU_TRY(h, cudaSetDevice(h->device));
   const cub_params& P = h->params;
   const Grid& g = h->g;
   const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0, cd = P.save_pixel_as_cell_data != 0;
   const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
   h->verts_per_cell = tri ? 3 : 4;
-  h->n_cells = tri ? 2 * h->n_quads : h->n_quads;
   h->id_bytes = id_bytes;
-  if (id_bytes == 4 && h->point_base + h->n_points > (1ull << 32))
-    return fail(h, CUB_ERR_OVERFLOW, "point ids up to %llu do not fit 32 bits", (unsigned long long)(h->point_base + h->n_points));
-
-  const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
-  CUB_TRY(ensure(h, h->cells, (size_t)h->n_cells * h->verts_per_cell * id_bytes));
-  if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, (size_t)h->n_quads));
-  if (cd) CUB_TRY(ensure(h, h->celldata, (size_t)h->n_cells * h->pix_bytes));
+  const size_t quad_bytes = (size_t)(tri ? 6 : 4) * id_bytes;   // cell bytes per quad
+  const size_t cd_bytes = (size_t)(tri ? 2 : 1) * h->pix_bytes;
+  if (exact) {
+    h->n_cells = tri ? 2 * h->n_quads : h->n_quads;
+    if (id_bytes == 4 && h->point_base + h->n_points > (1ull << 32))
+      return fail(h, CUB_ERR_OVERFLOW, "point ids up to %llu do not fit 32 bits", (unsigned long long)(h->point_base + h->n_points));
+    const size_t nq = (size_t)h->n_quads + (size_t)h->n_quads / 16;
+    CUB_TRY(ensure(h, h->cells, nq * quad_bytes));
+    if (mode == kEmitScratchQuads) CUB_TRY(ensure(h, h->quads, nq));
+    if (cd) CUB_TRY(ensure(h, h->celldata, nq * cd_bytes));
+  } else if (!h->cells.p || (mode == kEmitScratchQuads && !h->quads.p) || (cd && !h->celldata.p)) {
+    return kNeedSizes;
+  }
+  size_t quads_cap = h->cells.cap / quad_bytes;
+  if (mode == kEmitScratchQuads) quads_cap = std::min(quads_cap, h->quads.cap);
+  if (cd) quads_cap = std::min(quads_cap, h->celldata.cap / cd_bytes);
 
   if (h->timing) cudaEventRecord(h->ev[4], h->stream);
-  const bool ghost_points = (mode == kEmitScratchQuads) && h->ghost_v > 0;
-  const unsigned long long id_delta = (unsigned long long)h->point_base - (unsigned long long)h->ghost_v;
-  if (h->n_quads > 0) {
+  const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
+  // a second emit of the same count (another id width, new id bases) starts from unprojected points again
+  if (proj && h->projected) h->vertices_done = false;
+  if (!exact || h->n_quads > 0) {
     Timer t(h, 2);
-    if (!h->vertices_done) CUB_TRY(emit_vertex_stage(h));
+    if (!h->vertices_done) {
+      const int rc = emit_vertex_stage(h, exact);
+      if (rc != CUB_OK) return rc;
+    }
     {
-      // K3c: faces
+      // K3c: faces (the only consumer of the id base: a queued count exchange has to be through)
+      if (h->wait_before_faces) CU_TRY(h, cudaStreamWaitEvent(h->stream, h->wait_before_faces, 0));
       FaceArgs a{};
-      a.bits = h->bits.p; a.g = g; a.EY = h->EY; a.EW = h->EW;
+      a.bits = h->bits.p; a.g = g; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS;
       a.z_begin = h->zs0; a.z_end = h->zs1;
-      a.fofs = h->fofs.p; a.act = h->act.p; a.cofs = h->cofs.p; a.perm = h->raster ? nullptr : h->perm.p;
-      a.ghost_f = (uint32_t)h->ghost_f;
-      a.id_delta = id_delta;
+      a.act = h->act.p; a.seg = h->seg.p; a.perm = h->raster ? nullptr : h->perm.p;
+      a.info = h->d_info;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
+      a.quads_cap = quads_cap;
       a.mode = mode;
       a.vol = cd ? h->d_vol : nullptr;
       a.vX = h->gv.X; a.vY = h->gv.Y; a.vpad = h->pad; a.vzpad = h->zpad_lo;
@@ -774,20 +843,20 @@ int cub_emit(cub_handle h, int id_bytes) {
     }
     t.stop();
   }
-  if (proj && h->n_points > 0) {
+  if (proj && (!exact || h->n_points > 0)) {
     Timer t(h, 3);
-    const size_t start = ghost_points ? 0 : (size_t)h->ghost_v;
-    CUB_TRY(launch_project(h, h->points.p + 3 * start, n_pts_all - start));
+    CUB_TRY(launch_project(h, h->points.p, h->points.cap / 3, true, ghost_points));
+    h->projected = true;
     t.stop();
   }
-  if (mode == kEmitScratchQuads && h->n_quads > 0) {
+  if (mode == kEmitScratchQuads && (!exact || h->n_quads > 0)) {
     Timer t(h, 4);
-    const unsigned blocks = (unsigned)((h->n_quads + 255) / 256);
-    const unsigned long long delta = id_delta;
+    const size_t want = exact ? (size_t)h->n_quads : quads_cap;
+    const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((want + 255) / 256, (size_t)h->num_sms * 16));
     if (id_bytes == 4)
-      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, (size_t)h->n_quads, delta);
+      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, h->d_info, quads_cap);
     else
-      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, (size_t)h->n_quads, delta);
+      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, h->d_info, quads_cap);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();
@@ -798,8 +867,120 @@ int cub_emit(cub_handle h, int id_bytes) {
     cudaEventElapsedTime(&h->ms[6], h->ev[4], h->ev[5]);
   }
   h->emitted = true;
+  h->emit_unverified = !exact;
   return CUB_OK;
 }
+
+// after an emission that was queued without the host knowing the counts: learn them, and redo the emission with
+// buffers of the right size in the (rare) case that one was too small
+int verify_emit(cub_handle h) {
+  if (!h->counted) CUB_TRY(count_finish(h));
+  if (h->emit_unverified) {
+    h->emit_unverified = false;
+    const cub_params& P = h->params;
+    h->n_cells = P.generate_triangles ? 2 * h->n_quads : h->n_quads;
+    if (h->flags & kFlagBufferOverflow) {
+      h->vertices_done = false;
+      // (the id bases live on the device; finalize/the exchange wrote them, emit_launch does not touch them)
+      CUB_TRY(emit_launch(h, h->id_bytes, true));
+      CU_TRY(h, cudaStreamSynchronize(h->stream));
+    } else if (h->id_bytes == 4 && h->point_base + h->n_points > (1ull << 32)) {
+      return fail(h, CUB_ERR_OVERFLOW, "point ids up to %llu do not fit 32 bits", (unsigned long long)(h->point_base + h->n_points));
+    }
+  }
+  return CUB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cub_count(cub_handle h, const cub_params* p, uint64_t* n_points, uint64_t* n_quads) {
+  if (!h) return CUB_ERR_INVALID;
+  CUB_TRY(count_launch(h, p));
+  CUB_TRY(count_finish(h));
+  if (n_points) *n_points = h->n_points;
+  if (n_quads) *n_quads = h->n_quads;
+  return CUB_OK;
+}
+
+int cub_count_async(cub_handle h, const cub_params* p) {
+  if (!h) return CUB_ERR_INVALID;
+  return count_launch(h, p);
+}
+
+int cub_projection_halo(const cub_params* p, const double spacing[3], uint64_t* below, uint64_t* above) {
+  if (!p || !below || !above) return CUB_ERR_INVALID;
+  double sp[3] = {1.0, 1.0, 1.0};
+  if (spacing) for (int a = 0; a < 3; ++a) sp[a] = spacing[a];
+  if (!p->project_vertices) { *below = 2; *above = 1; return CUB_OK; }
+  double ms = sp[0];
+  for (int a = 1; a < 3; ++a) ms = sp[a] > ms ? sp[a] : ms;
+  const double step = p->step_length < 0.0 ? ms * 0.25 : p->step_length;
+  projection_reach(*p, step, sp[2], below, above);
+  return CUB_OK;
+}
+
+int cub_set_id_base(cub_handle h, uint64_t point_id_base, uint64_t cell_id_base) {
+  if (!h) return CUB_ERR_INVALID;
+  h->point_base = point_id_base;
+  h->cell_base = cell_id_base;
+  if (h->count_queued) {
+    CU_TRY(h, cudaSetDevice(h->device));
+    k_set_bases<<<1, 32, 0, h->stream>>>(h->d_info, point_id_base, cell_id_base);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
+  return CUB_OK;
+}
+
+int cub_emit_vertices(cub_handle h) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->count_queued) return fail(h, CUB_ERR_INVALID, "cub_emit_vertices before cub_count");
+  CU_TRY(h, cudaSetDevice(h->device));
+  if (h->vertices_done || h->timing) return CUB_OK;  // (per-kernel timing keeps the whole emission inside cub_emit)
+  const int rc = emit_vertex_stage(h, h->counted);
+  return rc == kNeedSizes ? CUB_OK : rc;  // (first run of an asynchronous pipeline: cub_emit_async sizes the buffers)
+}
+
+int cub_emit(cub_handle h, int id_bytes) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->count_queued) return fail(h, CUB_ERR_INVALID, "cub_emit before cub_count");
+  if (id_bytes != 4 && id_bytes != 8) return fail(h, CUB_ERR_INVALID, "id_bytes must be 4 or 8");
+  if (!h->counted) CUB_TRY(count_finish(h));
+  return emit_launch(h, id_bytes, true);
+}
+
+int cub_emit_async(cub_handle h, int id_bytes) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->count_queued) return fail(h, CUB_ERR_INVALID, "cub_emit_async before cub_count_async");
+  if (id_bytes != 4 && id_bytes != 8) return fail(h, CUB_ERR_INVALID, "id_bytes must be 4 or 8");
+  if (!h->counted && !h->timing) {
+    const int rc = emit_launch(h, id_bytes, false);
+    if (rc != kNeedSizes) return rc;
+  }
+  // first run (or per-kernel timing): the buffers have to be sized from the counts
+  if (!h->counted) CUB_TRY(count_finish(h));
+  return emit_launch(h, id_bytes, true);
+}
+
+int cub_finish(cub_handle h, uint64_t* n_points, uint64_t* n_cells) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!h->count_queued) return fail(h, CUB_ERR_INVALID, "cub_finish: nothing has been queued");
+  CUB_TRY(verify_emit(h));
+  if (!h->emit_unverified) CU_TRY(h, cudaStreamSynchronize(h->stream));
+  if (n_points) *n_points = h->n_points;
+  if (n_cells) *n_cells = h->params.generate_triangles ? 2 * h->n_quads : h->n_quads;
+  return CUB_OK;
+}
+
+int cub_device_counts(cub_handle h, const uint64_t** counts) {
+  if (!h || !counts) return CUB_ERR_INVALID;
+  *counts = reinterpret_cast<const uint64_t*>(h->d_info + kInfoPoints);
+  return CUB_OK;
+}
+
+const char* cub_last_warning(cub_handle h) { return h ? h->warning.c_str() : ""; }
 
 int cub_run(cub_handle h, const cub_params* p, int id_bytes, uint64_t* n_points, uint64_t* n_cells) {
   uint64_t np = 0, nq = 0;
@@ -814,6 +995,7 @@ int cub_fetch_async(cub_handle h, float* points, void* cells, void* cell_data, i
   if (!h) return CUB_ERR_INVALID;
   if (!h->emitted) return fail(h, CUB_ERR_INVALID, "cub_fetch before cub_emit");
   CU_TRY(h, cudaSetDevice(h->device));
+  CUB_TRY(verify_emit(h));
   const cudaMemcpyKind k = mem_kind == CUB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
   if (points && h->n_points)
     CU_TRY(h, cudaMemcpyAsync(points, h->points.p + 3 * (size_t)h->ghost_v, (size_t)h->n_points * 12, k, h->stream));
@@ -842,6 +1024,7 @@ int cub_device_buffers(cub_handle h, const float** points, const void** cells, c
                        uint64_t* n_points, uint64_t* n_cells, int* verts_per_cell, int* id_bytes) {
   if (!h) return CUB_ERR_INVALID;
   if (!h->emitted) return fail(h, CUB_ERR_INVALID, "no mesh has been emitted");
+  CUB_TRY(verify_emit(h));
   if (points) *points = h->points.p + 3 * (size_t)h->ghost_v;
   if (cells) *cells = h->cells.p;
   if (cell_data) *cell_data = h->params.save_pixel_as_cell_data ? h->celldata.p : nullptr;
@@ -854,7 +1037,7 @@ int cub_device_buffers(cub_handle h, const float** points, const void** cells, c
 
 int cub_debug_bitmask(cub_handle h, uint32_t* out, uint64_t* words_per_row) {
   if (!h) return CUB_ERR_INVALID;
-  if (!h->counted) return fail(h, CUB_ERR_INVALID, "cub_debug_bitmask before cub_count");
+  if (!h->count_queued) return fail(h, CUB_ERR_INVALID, "cub_debug_bitmask before cub_count");
   if (h->pad) return fail(h, CUB_ERR_UNSUPPORTED, "cub_debug_bitmask: the bitmask of image_border_faces runs is that of the padded image");
   if (words_per_row) *words_per_row = (uint64_t)h->g.Wp;
   if (out) {
@@ -873,10 +1056,10 @@ int cub_debug_project_points(cub_handle h, const cub_params* p, float* points_xy
   h->params = *p;
   CUB_TRY(setup_grid(h));
   compute_step(h);
-  h->counted = h->emitted = false;
+  h->counted = h->emitted = h->count_queued = false;
   CUB_TRY(ensure(h, h->points, 3 * (size_t)n_points));
   CU_TRY(h, cudaMemcpyAsync(h->points.p, points_xyz, (size_t)n_points * 12, cudaMemcpyHostToDevice, h->stream));
-  CUB_TRY(launch_project(h, h->points.p, (size_t)n_points));
+  CUB_TRY(launch_project(h, h->points.p, (size_t)n_points, false, true));
   CU_TRY(h, cudaMemcpyAsync(points_xyz, h->points.p, (size_t)n_points * 12, cudaMemcpyDeviceToHost, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
   return CUB_OK;
@@ -903,7 +1086,7 @@ int cub_generate_volume(cub_handle h, int kind, const uint64_t dims[3], const ui
   a.p0 = (float)param0; a.p1 = (float)param1;
   a.seed = seed;
   size_t blocks = (n + 255) / 256;
-  if (blocks > (size_t)kNumSMs * 32) blocks = (size_t)kNumSMs * 32;
+  if (blocks > (size_t)h->num_sms * 32) blocks = (size_t)h->num_sms * 32;
   k_generate<<<(unsigned)blocks, 256, 0, h->stream>>>(a);
   h->launches++;
   CU_TRY(h, cudaGetLastError());
@@ -928,6 +1111,34 @@ int cub_download_volume(cub_handle h, void* out, uint64_t bytes) {
   return CUB_OK;
 }
 
+// Device memory for callers that do not link the CUDA runtime themselves (the destination buffers of
+// cub_comm_gather_mesh, CUB_MEM_DEVICE volumes): plain cudaMalloc / cudaFree / cudaMemcpyAsync on the handle's device.
+int cub_device_alloc(cub_handle h, uint64_t bytes, void** out) {
+  if (!h || !out) return CUB_ERR_INVALID;
+  *out = nullptr;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaMalloc(out, bytes ? (size_t)bytes : 1));
+  return CUB_OK;
+}
+
+int cub_device_free(cub_handle h, void* p) {
+  if (!h) return CUB_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaFree(p));
+  return CUB_OK;
+}
+
+int cub_device_copy(cub_handle h, void* dst, const void* src, uint64_t bytes, int dst_kind, int src_kind) {
+  if (!h || (!dst && bytes) || (!src && bytes)) return CUB_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  const cudaMemcpyKind k = dst_kind == CUB_MEM_DEVICE ? (src_kind == CUB_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice)
+                                                      : (src_kind == CUB_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
+  CU_TRY(h, cudaMemcpyAsync(dst, src, (size_t)bytes, k, h->stream));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CUB_OK;
+}
+
 int cub_enable_timing(cub_handle h, int on) {
   if (!h) return CUB_ERR_INVALID;
   h->timing = on != 0;
@@ -943,3 +1154,5 @@ int cub_get_timings(cub_handle h, float ms[8]) {
 uint64_t cub_launch_count(cub_handle h) { return h ? h->launches : 0; }
 
 }  // extern "C"
+
+#include "cuberille_comm.inl"

@@ -16,9 +16,9 @@
 // Lanes past the end of a ragged row re-read the row's last voxel, which produces the "replicate
 // bit X-1" padding the later kernels rely on (generic path only).
 #pragma once
-#include "cub_common.cuh"
+#include "cbr_common.cuh"
 
-namespace cub {
+namespace cbr {
 
 constexpr int kWordsPerTask = 16;
 
@@ -167,4 +167,4 @@ __global__ void __launch_bounds__(256) k_classify_padded(const T* __restrict__ v
   }
 }
 
-}  // namespace cub
+}  // namespace cbr

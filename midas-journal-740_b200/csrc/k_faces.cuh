@@ -3,30 +3,32 @@
 //
 // Reference: faceHasQuad (txx:164-173), the face -> corner table (txx:197-202, 219-233) and AddQuadFace
 // (txx:279-332).  Cell ids follow voxel raster x face index (nextCellId, txx:117): cell index =
-// fofs[word] + rank inside the word.  The four vertex ids of a face come from the corner -> id map:
-//     slot(corner) = cofs[corner word] + popc(act[corner word] & bits below)      id = perm[slot]
-// where the corner words around the voxel word are loaded once per word, up front together with the bitmask
-// words (the kernel is bound by its chain of dependent loads, not by bytes).  The surface voxels of a warp's
-// 32 words are then compacted into a shared-memory queue and emitted one voxel per lane.
+// face base of the word + rank inside the word.  The four vertex ids of a face come from the corner -> id map:
+//     slot(corner) = slot base of the corner word + popc(act[corner word] & bits below)      id = perm[slot]
+// A warp owns one 32-word segment of a voxel row; the face base and the slot bases of the four corner rows
+// around it are the segment bases of k_seg_scan plus warp scans of the face counts / popc(act) the lanes hold
+// anyway (round 1 read them from three dense offset arrays).  The act words are loaded once per word, up front
+// together with the bitmask words (the kernel is bound by its chain of dependent loads, not by bytes).  The
+// surface voxels of a warp's 32 words are then compacted into a shared-memory queue and emitted one voxel per lane.
 #pragma once
-#include "cub_common.cuh"
+#include "cbr_common.cuh"
+#include "k_segscan.cuh"
 
-namespace cub {
+namespace cbr {
 
 enum { kEmitQuads = 0, kEmitTrisFixed = 1, kEmitScratchQuads = 2 };
 
 struct FaceArgs {
   const uint32_t* bits;
   Grid g;
-  int EY, EW;
+  int EY, EW, NS;
   int z_begin, z_end;          // local voxel slices whose faces are emitted (the handle's own range)
-  const uint32_t* fofs;        // entry lattice, exclusive scan of face counts
   const uint32_t* act;
-  const uint32_t* cofs;
+  const uint4* seg;            // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   const uint32_t* perm;        // slot -> scan-relative vertex id
-  uint32_t ghost_f;            // scan offset of the first own face
-  unsigned long long id_delta; // scan-relative vertex id -> final id (mod 2^64)
+  const unsigned long long* info;  // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
   void* cells;                 // final cells (IdT) or scratch quads (uint32 scan-relative ids)
+  size_t quads_cap;            // quads the cell buffer can hold
   int mode;                    // kEmit*
   const void* vol;             // for cell data (may be null)
   int vX, vY, vpad, vzpad;     // cell data: buffer row / slice size; lattice (x, y, z) is voxel (x - vpad, y - vpad, z - vzpad)
@@ -51,12 +53,14 @@ __device__ __forceinline__ void store_tri_pair(IdT* c, IdT a0, IdT a1, IdT a2, I
 }
 
 template <typename IdT, int MODE>
-__device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
+__device__ __forceinline__ void write_cell(const FaceArgs& a, unsigned long long id_delta, uint32_t fidx, uint32_t q0,
+                                           uint32_t q1, uint32_t q2, uint32_t q3) {
+  if (fidx >= a.quads_cap) return;  // (only when the caller queued the emission before it knew the counts: flagged by the kernel)
   if (MODE == kEmitScratchQuads) {
     reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4(q0, q1, q2, q3);
     return;
   }
-  const IdT v0 = (IdT)(q0 + a.id_delta), v1 = (IdT)(q1 + a.id_delta), v2 = (IdT)(q2 + a.id_delta), v3 = (IdT)(q3 + a.id_delta);
+  const IdT v0 = (IdT)(q0 + id_delta), v1 = (IdT)(q1 + id_delta), v2 = (IdT)(q2 + id_delta), v3 = (IdT)(q3 + id_delta);
   IdT* c = reinterpret_cast<IdT*>(a.cells);
   if (MODE == kEmitQuads) {
     c += (size_t)fidx * 4;
@@ -86,6 +90,7 @@ __device__ __forceinline__ unsigned long long load_pixel(const void* vol, size_t
 
 template <int MODE>
 __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx, unsigned long long pix) {
+  if (fidx >= a.quads_cap) return;
   const bool two = (MODE != kEmitQuads);
   const size_t c = two ? 2 * (size_t)fidx : (size_t)fidx;
   switch (a.pix_bytes) {
@@ -98,11 +103,11 @@ __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx,
 
 constexpr int kFaceThreads = 128;
 
-// per-word context a warp shares through shared memory: 5 x uint4
+// per-word context a warp shares through shared memory: 4 x uint4
 //   [0] A[oz][oy]   active masks of the 4 corner words       [1] C[oz][oy]  their slot bases
-//   [2] Cn[oz][oy]  slot bases of the corner words at w+1     [3] F0..F3     [4] F4, F5, face base, -
+//   [2] F0..F3      [3] F4, F5, face base, -
 struct FaceSmem {
-  uint4 ctx[kFaceThreads / 32][32][5];
+  uint4 ctx[kFaceThreads / 32][32][4];
   uint16_t queue[kFaceThreads / 32][1024];         // (lane << 5) | bit of every surface voxel of the warp's words
 };
 
@@ -117,19 +122,25 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   // grid: x = 32-word segments of a row, y = groups of 4 rows (one row per warp), z = own slices.  128-thread CTAs:
   // a CTA keeps its registers and shared memory until its last warp is done, and warps differ a lot here (r1: 256
   // threads 1.127 ms of emission, 128 threads 1.084, 64 threads 1.121)
-  const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kFaceThreads / 32) + warp, zl = a.z_begin + blockIdx.z;
+  const int sgm = blockIdx.x, w = sgm * 32 + lane, y = blockIdx.y * (kFaceThreads / 32) + warp, zl = a.z_begin + blockIdx.z;
 
   // ---- face masks of the word (txx:164-173; clamped neighbours: no face on the image border) --------------
   uint32_t F[6] = {0, 0, 0, 0, 0, 0};
-  // context of the word: active masks and slot bases of the 4 corner words around it (index oz*2+oy), the slot
-  // bases of the corner words at w+1 (the next lane's, except at the end of the segment), first face index
+  // context of the word: active masks of the 4 corner words around it (index oz*2+oy) and the segment bases of
+  // their rows {-, faces, active corners, -}
   const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
   const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
-  uint32_t A[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0}, Cn[4] = {0, 0, 0, 0}, fbase = 0;
+  uint32_t A[4] = {0, 0, 0, 0};
+  uint4 sb[4] = {};
   {
     // all the words are requested together (no early-out on an empty word: that would make the neighbour
     // loads wait for the first one, and the kernel is bound by its chain of dependent loads)
     const bool valid = w < g.Wx && y < g.Y;
+    if (y < g.Y) {
+      const size_t r0 = (size_t)zl * a.EY + y;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) sb[k] = __ldg(a.seg + (r0 + (size_t)(k >> 1) * a.EY + (k & 1)) * a.NS + sgm);
+    }
     // word and entry indices fit 32 bits (cub_count checks the lattice size): one IMAD.WIDE per load
     const uint32_t* __restrict__ row = a.bits + (((uint32_t)zl * (uint32_t)g.Y + (uint32_t)y) * (uint32_t)g.Wp + (uint32_t)w);
     const int zgl = zl + g.zg0;
@@ -140,13 +151,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     uint32_t c0 = 0, nym = 0, nyp = 0, nzm = 0, nzp = 0, edge = 0;
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
-        A[k] = __ldg(a.act + e);
-        C[k] = __ldg(a.cofs + e);
-        if (lane == 31 || w == g.Wx - 1) Cn[k] = __ldg(a.cofs + e + 1u);  // (the next lane has no voxel word: it loads nothing)
-      }
-      fbase = __ldg(a.fofs + e00);
+      for (int k = 0; k < 4; ++k) A[k] = __ldg(a.act + e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW));
       c0 = __ldg(row);
       nym = __ldg(row + dym); nyp = __ldg(row + dyp); nzm = __ldg(row + dzm); nzp = __ldg(row + dzp);
       // the x neighbours are the adjacent lanes' words, except across the ends of the warp's 32-word segment
@@ -154,11 +159,6 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
       if (lane == 31 && w < g.Wx - 1) edge = __ldg(row + 1);
     }
     const uint32_t up = __shfl_up_sync(0xffffffffu, c0, 1), dn = __shfl_down_sync(0xffffffffu, c0, 1);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t nx = __shfl_down_sync(0xffffffffu, C[k], 1);
-      if (lane != 31 && w != g.Wx - 1) Cn[k] = nx;
-    }
     if (valid) {
       const uint32_t XB = g.X & 31;
       const uint32_t vc = (w == g.Wx - 1 && XB) ? ((1u << XB) - 1u) : ~0u;
@@ -175,23 +175,30 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   }
   uint32_t U = F[0] | F[1] | F[2] | F[3] | F[4] | F[5];
   const uint32_t nvox = __popc(U);
-  uint32_t incl = nvox;
+  const uint32_t nf = __popc(F[0]) + __popc(F[1]) + __popc(F[2]) + __popc(F[3]) + __popc(F[4]) + __popc(F[5]);
+  // warp scans in 16-bit fields: surface voxels (queue positions) | faces (cell ids); active corners of the
+  // four corner rows (slots)
+  uint32_t s0 = nvox | (nf << 16);
+  uint32_t s1 = (uint32_t)__popc(A[0]) | ((uint32_t)__popc(A[1]) << 16), s2 = (uint32_t)__popc(A[2]) | ((uint32_t)__popc(A[3]) << 16);
+  const uint32_t m0 = s0, m1 = s1, m2 = s2;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += v;
+    const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
+    if (lane >= o) { s0 += t0; s1 += t1; s2 += t2; }
   }
-  const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-  if (total == 0) return;  // most warps: no surface voxel in 1024 voxels
+  const uint32_t total = __shfl_sync(0xffffffffu, s0, 31) & 0xffffu;
+  if (total == 0) return;  // no surface voxel in the 1024 voxels of the segment
+  const unsigned long long id_delta = __ldg(a.info + kInfoIdDelta);
+  const uint32_t ghost_f = (uint32_t)__ldg(a.info + kInfoMarkF);
 
   if (U) {
+    s0 -= m0; s1 -= m1; s2 -= m2;  // exclusive
     uint4* cx = sm.ctx[warp][lane];
     cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
-    cx[1] = make_uint4(C[0], C[1], C[2], C[3]);
-    cx[2] = make_uint4(Cn[0], Cn[1], Cn[2], Cn[3]);
-    cx[3] = make_uint4(F[0], F[1], F[2], F[3]);
-    cx[4] = make_uint4(F[4], F[5], fbase - a.ghost_f, 0u);
-    uint32_t pos = incl - nvox;
+    cx[1] = make_uint4(sb[0].z + (s1 & 0xffffu), sb[1].z + (s1 >> 16), sb[2].z + (s2 & 0xffffu), sb[3].z + (s2 >> 16));
+    cx[2] = make_uint4(F[0], F[1], F[2], F[3]);
+    cx[3] = make_uint4(F[4], F[5], sb[0].y + (s0 >> 16) - ghost_f, 0u);
+    uint32_t pos = s0 & 0xffffu;
     uint16_t* q = sm.queue[warp];
     const uint32_t tag = (uint32_t)lane << 5;
     while (U) {
@@ -202,12 +209,13 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   }
   __syncwarp();
 
+  bool overflow = false;
   for (uint32_t s = lane; s < total; s += 32) {
     const uint32_t it = sm.queue[warp][s];
     const uint32_t src = it >> 5, b = it & 31u;
     const uint4* cx = sm.ctx[warp][src];
-    const uint4 A4 = cx[0], C4 = cx[1], N4 = cx[2], Fa = cx[3], Fb = cx[4];
-    const uint32_t A[4] = {A4.x, A4.y, A4.z, A4.w}, C[4] = {C4.x, C4.y, C4.z, C4.w}, Cn[4] = {N4.x, N4.y, N4.z, N4.w};
+    const uint4 A4 = cx[0], C4 = cx[1], Fa = cx[2], Fb = cx[3];
+    const uint32_t A[4] = {A4.x, A4.y, A4.z, A4.w}, C[4] = {C4.x, C4.y, C4.z, C4.w};
     const uint32_t Fm[6] = {Fa.x, Fa.y, Fa.z, Fa.w, Fb.x, Fb.y};
     const uint32_t bit = 1u << b, below = bit - 1u;
     // index of the voxel's first face: faces of the voxels before it in the word
@@ -220,7 +228,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     for (int k = 0; k < 4; ++k) {
       const int oz = k >> 1, oy = k & 1;
       const uint32_t s0 = C[k] + __popc(A[k] & below);                      // corner x
-      const uint32_t s1 = (b == 31) ? Cn[k] : s0 + ((A[k] >> b) & 1u);      // corner x+1
+      const uint32_t s1 = s0 + ((A[k] >> b) & 1u);                          // corner x+1 (b = 31: bit 0 of the next corner word)
       vid[oz * 4 + (oy ? 3 : 0)] = s0;
       vid[oz * 4 + (oy ? 2 : 1)] = s1;
     }
@@ -236,14 +244,16 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     // the voxel behind the face (cell data): word src of this warp's row
     const unsigned long long voxel =
         CD ? load_pixel(a.vol, ((size_t)(zl - a.vzpad) * a.vY + (size_t)(y - a.vpad)) * a.vX +
-                                           (size_t)((blockIdx.x * 32 + src) * 32 + b - a.vpad), a.pix_bytes) : 0ull;
-    if (f0) { write_cell<IdT, MODE>(a, fi, vid[0], vid[4], vid[7], vid[3]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f1) { write_cell<IdT, MODE>(a, fi, vid[0], vid[1], vid[5], vid[4]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f2) { write_cell<IdT, MODE>(a, fi, vid[1], vid[2], vid[6], vid[5]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f3) { write_cell<IdT, MODE>(a, fi, vid[2], vid[3], vid[7], vid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f4) { write_cell<IdT, MODE>(a, fi, vid[0], vid[3], vid[2], vid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f5) { write_cell<IdT, MODE>(a, fi, vid[4], vid[5], vid[6], vid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+                                           (size_t)((sgm * 32 + src) * 32 + b - a.vpad), a.pix_bytes) : 0ull;
+    if (f0) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[4], vid[7], vid[3]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f1) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[1], vid[5], vid[4]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f2) { write_cell<IdT, MODE>(a, id_delta, fi, vid[1], vid[2], vid[6], vid[5]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f3) { write_cell<IdT, MODE>(a, id_delta, fi, vid[2], vid[3], vid[7], vid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f4) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[3], vid[2], vid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f5) { write_cell<IdT, MODE>(a, id_delta, fi, vid[4], vid[5], vid[6], vid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    overflow |= fi > a.quads_cap;
   }
+  if (overflow) atomicOr(const_cast<unsigned long long*>(a.info) + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
 }
 
 // K5: triangle split of projected quads (AddQuadFace txx:286-321): reads the four PROJECTED points
@@ -251,31 +261,35 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
 // `>=` tie -> first split.
 template <typename IdT>
 __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ quads, const float* __restrict__ points,
-                                                     IdT* __restrict__ tris, size_t n_quads,
-                                                     unsigned long long id_delta) {
-  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_quads) return;
-  const uint4 q = quads[i];
-  const uint32_t id[4] = {q.x, q.y, q.z, q.w};
-  float p[4][3];
+                                                     IdT* __restrict__ tris, const unsigned long long* __restrict__ info,
+                                                     size_t quads_cap) {
+  // the number of quads and the id offset come from the device-side run info (no host round trip needed)
+  const size_t n_all = (size_t)__ldg(info + kInfoQuads);
+  const size_t n_quads = n_all < quads_cap ? n_all : quads_cap;
+  const unsigned long long id_delta = __ldg(info + kInfoIdDelta);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 q = quads[i];
+    const uint32_t id[4] = {q.x, q.y, q.z, q.w};
+    float p[4][3];
 #pragma unroll
-  for (int k = 0; k < 4; ++k)
+    for (int k = 0; k < 4; ++k)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[k][c] = __ldg(points + 3 * (size_t)id[k] + c);
-  double d02 = 0.0, d13 = 0.0;
+      for (int c = 0; c < 3; ++c) p[k][c] = __ldg(points + 3 * (size_t)id[k] + c);
+    double d02 = 0.0, d13 = 0.0;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const double a = __dadd_rn((double)p[0][c], -(double)p[2][c]);
-    d02 = __dadd_rn(d02, __dmul_rn(a, a));
-    const double b = __dadd_rn((double)p[1][c], -(double)p[3][c]);
-    d13 = __dadd_rn(d13, __dmul_rn(b, b));
+    for (int c = 0; c < 3; ++c) {
+      const double a = __dadd_rn((double)p[0][c], -(double)p[2][c]);
+      d02 = __dadd_rn(d02, __dmul_rn(a, a));
+      const double b = __dadd_rn((double)p[1][c], -(double)p[3][c]);
+      d13 = __dadd_rn(d13, __dmul_rn(b, b));
+    }
+    IdT v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = (IdT)((unsigned long long)id[k] + id_delta);
+    IdT* c = tris + i * 6;
+    const bool first = d02 >= d13;  // (0,1,3),(1,2,3) else (0,1,2),(0,2,3)
+    store_tri_pair<IdT>(c, v[0], v[1], first ? v[3] : v[2], first ? v[1] : v[0], v[2], v[3]);
   }
-  IdT v[4];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) v[k] = (IdT)((unsigned long long)id[k] + id_delta);
-  IdT* c = tris + i * 6;
-  const bool first = d02 >= d13;  // (0,1,3),(1,2,3) else (0,1,2),(0,2,3)
-  store_tri_pair<IdT>(c, v[0], v[1], first ? v[3] : v[2], first ? v[1] : v[0], v[2], v[3]);
 }
 
-}  // namespace cub
+}  // namespace cbr

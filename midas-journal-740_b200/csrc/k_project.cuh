@@ -16,9 +16,10 @@
 #pragma once
 #include <climits>
 
-#include "cub_common.cuh"
+#include "cbr_common.cuh"
+#include "k_segscan.cuh"
 
-namespace cub {
+namespace cbr {
 
 struct ProjArgs {
   const void* vol;
@@ -30,7 +31,9 @@ struct ProjArgs {
   double relax;  // m_ProjectVertexStepLengthRelaxationFactor
   unsigned max_steps;
   float* points;
-  size_t n_points;
+  size_t n_points;           // number of points, or (info != null) the capacity of the point buffer
+  const unsigned long long* info;  // when set: the points are [ghost ? 0 : info[kInfoGhostV], info[kInfoGhostV] + info[kInfoPoints])
+  int include_ghost;
   long long i0[3];           // image index of buffer voxel (0, 0, 0) (cub_set_region_index): continuous indices are image indices
   unsigned long long* work;  // device counter (zeroed before the launch): next vertex to hand out
 };
@@ -96,6 +99,14 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     inv_sp[k] = 1.0 / a.geom.spacing[k];
     gc[k] = (float)(0.5 * inv_sp[k]);
   }
+  size_t n_points = a.n_points;
+  float* const points = a.points + (a.info && !a.include_ghost ? 3 * (size_t)__ldg(a.info + kInfoGhostV) : 0);
+  if (a.info) {
+    const size_t ghost = (size_t)__ldg(a.info + kInfoGhostV);
+    size_t all = ghost + (size_t)__ldg(a.info + kInfoPoints);
+    if (all > a.n_points) all = a.n_points;
+    n_points = a.include_ghost ? all : (all > ghost ? all - ghost : 0);
+  }
   size_t i = 0;
   bool have = false;
   float vert[3] = {0.f, 0.f, 0.f};
@@ -112,8 +123,8 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   while (true) {
     if (!have) {
       i = (size_t)atomicAdd(a.work, 1ull);
-      if (i >= a.n_points) break;
-      vert[0] = a.points[3 * i]; vert[1] = a.points[3 * i + 1]; vert[2] = a.points[3 * i + 2];
+      if (i >= n_points) break;
+      vert[0] = points[3 * i]; vert[1] = points[3 * i + 1]; vert[2] = points[3 * i + 2];
       step = a.step0;
       numberOfSteps = 0;
       have = true;
@@ -241,12 +252,12 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
       }
     }
     if (done) {
-      a.points[3 * i] = vert[0];
-      a.points[3 * i + 1] = vert[1];
-      a.points[3 * i + 2] = vert[2];
+      points[3 * i] = vert[0];
+      points[3 * i + 1] = vert[1];
+      points[3 * i + 2] = vert[2];
       have = false;
     }
   }
 }
 
-}  // namespace cub
+}  // namespace cbr

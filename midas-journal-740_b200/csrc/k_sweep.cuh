@@ -1,5 +1,4 @@
-// k_sweep.cuh — K2a (count) and K3a (assign): corner-centric ownership, shared through shared memory,
-// swept along z.
+// k_sweep.cuh — K2a: corner-centric first-touch ownership, shared through shared memory, swept along z.
 //
 // Reference: the "Create vertices" part of the hot loop (txx:179-194) and the two-plane vertex lookup it
 // relies on (VertexLookupMap h:273-313, txx:128-131,155-161,186-191).
@@ -21,19 +20,16 @@
 // the R+1 voxel rows under its corner rows for the new slice (one step ahead of their use), evaluates the
 // closed form for corner plane z+1, publishes what its -x / -y neighbours need (6 words per thread,
 // whatever R), and assembles the 8 ownership masks of its R voxel words in slice z.
-//   MODE_COUNT  (K2a): per entry of the [Zl+1][Y+1][EW] lattice one packed count
-//                      (owned corners | faces << 10 | active corners << 20), the active-corner mask and, for
-//                      words that own a corner, the 8 ownership masks themselves (k_assign.cuh walks them)
-//   MODE_ASSIGN (K3a, first version, kept behind CUB_ASSIGN_SWEEP=1): a second sweep that walks the owned corners of every voxel word in reference order (voxel bit, then local
-//                      corner 0..7, txx:179-194) and records, at vertex id = vofs[word] + rank, WHICH lattice
-//                      corner that vertex is (packed coordinates); k_vertices.cuh turns that into points and
-//                      the corner -> id map the face kernel reads
+// Output per entry of the [Zl+1][EY][EW] lattice: one packed count (owned corners | faces << 10 | active corners << 20),
+// the active-corner mask and, for words that own a corner, the 8 ownership masks themselves (k_vertices.cuh walks
+// them).  Round 1 also had a second instantiation that swept the volume again to number the vertices; storing the
+// masks made it redundant (0.52 ms against 0.07 ms here) and it is gone.
 #pragma once
-#include "cub_common.cuh"
+#include "cbr_common.cuh"
 
-namespace cub {
+namespace cbr {
 
-enum { MODE_COUNT = 0, MODE_ASSIGN = 1 };
+enum { MODE_COUNT = 0 };
 
 struct SweepArgs {
   const uint32_t* bits;
@@ -47,10 +43,7 @@ struct SweepArgs {
   uint32_t* act;       // [Zl+1][EY][EW] active-corner mask of the corner word
   uint4* own;          // [Zl+1][EY][EW][2] the 8 ownership masks of the voxel word, written where it owns a corner
                        // (may be null: raster vertex order does not need them)
-  // --- assign
-  const uint32_t* vofs;      // [Zl+1][EY][EW] exclusive scan of the owned-corner counts
-  uint32_t* vtx;             // [n vertices] cx | cy << 16 | oz << 31  (oz: the corner is on the owner slice's upper plane;
-                             //  the owner slice follows from the id: ids of a slice are contiguous, k_vertices.cuh)
+  uint32_t* slice_any;  // [Zl] set to 1 where voxel slice z has an inside voxel (the empty-interior-slice check), may be null
 };
 
 template <int NTX_, int NTY_, int R_, int MODE_>
@@ -170,9 +163,6 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
   fetch_slice(zs - 1, nx_c, nx_p);
   decode_slice(nx_c, nx_p, hi_c, hi_l);
   fetch_slice(zs, nx_c, nx_p);
-  uint32_t vnx[R];                    // prefetched scan offsets of the voxel words of the next assembled slice
-#pragma unroll
-  for (int k = 0; k < R; ++k) vnx[k] = 0;
   // kept from the previous plane: own P4..P7 per row, the +y neighbour's P4,P5, the neighbours' nibbles, active masks
   uint32_t sv[R][4], su4 = 0, su5 = 0, nr_prev = 0, nur_prev = 0, act_prev[R];
 #pragma unroll
@@ -190,17 +180,6 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
     for (int k = 0; k <= R; ++k) { lo_c[k] = hi_c[k]; lo_l[k] = hi_l[k]; }
     decode_slice(nx_c, nx_p, hi_c, hi_l);
     if (cz < ze) fetch_slice(cz + 1, nx_c, nx_p);
-    uint32_t vpre[R];
-    if (MODE == MODE_ASSIGN) {
-#pragma unroll
-      for (int k = 0; k < R; ++k) vpre[k] = vnx[k];
-      if (cz < ze) {  // the next step assembles slice cz
-        const uint32_t* __restrict__ vz = a.vofs + (size_t)cz * plane_entries;
-#pragma unroll
-        for (int k = 0; k < R; ++k)
-          if ((rowok_bits >> k) & 1u) vnx[k] = __ldg(vz + e0 + k * a.EW);
-      }
-    }
     const int czg = cz + g.zg0;
     uint32_t own[R][8];
     uint32_t nib = 0;
@@ -238,7 +217,13 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
       exw[4 * NT] = lo_c[1];
       exw[5 * NT] = nib;
     }
-    __syncthreads();
+    // (the barrier also tells whether slice cz-1 has an inside voxel at all: the empty-interior-slice check)
+    uint32_t any_in = 0;
+#pragma unroll
+    for (int k = 0; k < R; ++k)
+      if ((rowok_bits >> k) & 1u) any_in |= lo_c[k + 1] & vc;
+    const int slice_occupied = __syncthreads_or(any_in != 0);
+    if (t == 0 && slice_occupied && cz > zs && a.slice_any) a.slice_any[cz - 1] = 1u;
 
     uint32_t act[R];
 #pragma unroll
@@ -316,34 +301,6 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
             }
           }
         }
-      } else {
-        // vertex id -> lattice corner, in the reference's creation order inside the word
-#pragma unroll
-        for (int k = 0; k < R; ++k) {
-          if (!((rowok_bits >> k) & 1u)) continue;
-          uint32_t O[8];
-          assemble(k, O);
-          uint32_t U = O[0] | O[1] | O[2] | O[3] | O[4] | O[5] | O[6] | O[7];
-          if (U) {
-            uint32_t* __restrict__ const out = a.vtx;
-            uint32_t n = vpre[k];   // a 32-bit index: a predicated 64-bit pointer bump costs 6 instructions here
-            const uint32_t xy0 = (uint32_t)(cw * 32) | ((uint32_t)(cy0 + k) << 16);
-            while (U) {
-              const int b = __ffs(U) - 1;
-              U &= U - 1;
-              const uint32_t bit = 1u << b;
-              const uint32_t xy = xy0 + (uint32_t)b;
-              if (O[0] & bit) { out[n] = xy; ++n; }
-              if (O[1] & bit) { out[n] = xy + 1u; ++n; }
-              if (O[2] & bit) { out[n] = xy + 0x10001u; ++n; }
-              if (O[3] & bit) { out[n] = xy + 0x10000u; ++n; }
-              if (O[4] & bit) { out[n] = xy + 0x80000000u; ++n; }
-              if (O[5] & bit) { out[n] = xy + 0x80000001u; ++n; }
-              if (O[6] & bit) { out[n] = xy + 0x80010001u; ++n; }
-              if (O[7] & bit) { out[n] = xy + 0x80010000u; ++n; }
-            }
-          }
-        }
       }
     }
 
@@ -358,4 +315,4 @@ __global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
   }
 }
 
-}  // namespace cub
+}  // namespace cbr
