@@ -35,7 +35,7 @@ enum {
   CUB_ERR_CUDA = 2,       /* a CUDA runtime call failed (see cub_last_error)  */
   CUB_ERR_NOMEM = 3,      /* device or pinned-host allocation failed          */
   CUB_ERR_OVERFLOW = 4,   /* ids do not fit the requested id width            */
-  CUB_ERR_UNSUPPORTED = 5 /* e.g. oblique direction matrix                    */
+  CUB_ERR_UNSUPPORTED = 5 /* e.g. an image too wide for one handle, no NCCL    */
 };
 
 /* ---- pixel types: TInputImage::PixelType (h:150) ------------------------ */
@@ -105,8 +105,15 @@ const char *cub_last_error(cub_handle h);
  *   mem_kind  : CUB_MEM_HOST -> copied to the device on the handle's stream;
  *               CUB_MEM_DEVICE -> borrowed (must stay valid until the next
  *               cub_set_volume / cub_destroy), no copy
- *   direction : row-major 3x3; only the identity is supported (the reference's
- *               half-spacing shift txx:268-270 is axis-aligned anyway)
+ *   direction : row-major 3x3 direction cosines (itk::ImageBase::GetDirection), or
+ *               NULL = identity.  The identity is the non-oriented image every test
+ *               of the reference has.  Any other (non-singular) matrix gives the
+ *               oriented-image semantics of ITK: TransformIndexToPhysicalPoint with
+ *               M = direction*diag(spacing) into the float point (txx:266), the
+ *               continuous index through M^-1, gradients rotated into physical
+ *               space (GradientImageFilter's UseImageDirection); the reference's
+ *               half-spacing shift stays axis-aligned in physical space, exactly as
+ *               written at txx:268-270.
  * The volume may be a z-slab of a larger image, see cub_set_slab.              */
 int cub_set_volume(cub_handle h, const void *data, int dtype, const uint64_t dims[3],
                    const double spacing[3], const double origin[3],

@@ -46,8 +46,10 @@ __device__ __constant__ const int8_t kFaceCorners[6][4] = {{0, 4, 7, 3}, {0, 1, 
 struct Geom {
   double spacing[3];
   double origin[3];
-  // oriented images (a non-identity direction matrix): index -> physical matrix M = direction * diag(spacing)
-  // and its inverse, both row-major; unused (and the ITK 3.x expressions are evaluated) when oriented == 0
+  // oriented images (a non-identity direction matrix): the direction cosines D, the index -> physical matrix
+  // M = D * diag(spacing) and its inverse, all row-major; unused (the ITK 3.x expressions are evaluated) when
+  // oriented == 0
+  double dir[9];
   double m[9];
   double minv[9];
   int oriented;

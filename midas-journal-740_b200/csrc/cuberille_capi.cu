@@ -109,7 +109,9 @@ struct cub_handle_s {
   bool slab_set = false;
 
   // scratch
-  DevBuf<uint32_t> bits, cnt, act, perm, slice_any;
+  DevBuf<uint32_t> bits, cnt, act, cofs, perm, slice_any;
+  DevBuf<uint32_t> vtx;      // K3a -> K3b: the lattice corner of every vertex id
+  DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
   DevBuf<uint4> own;         // K2a -> K3a: the 8 ownership masks per voxel word (2 x uint4 per entry)
   DevBuf<uint4> seg;         // K2b -> K3: segment bases {vertices, faces, active corners, -}
   int EY = 0, EW = 0, NS = 0;
@@ -433,7 +435,7 @@ int cub_destroy(cub_handle h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
   cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->perm.p); cudaFree(h->own.p); cudaFree(h->seg.p);
-  cudaFree(h->slice_any.p); cudaFree(h->status.p);
+  cudaFree(h->slice_any.p); cudaFree(h->status.p); cudaFree(h->cofs.p); cudaFree(h->vtx.p); cudaFree(h->vsl.p);
   cudaFree(h->d_ticket); cudaFree(h->d_info);
   if (h->h_info) cudaFreeHost(h->h_info);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
@@ -452,17 +454,37 @@ static int set_geometry(cub_handle h, int dtype, const uint64_t dims[3], const d
   if (!pb) return fail(h, CUB_ERR_INVALID, "unknown dtype %d", dtype);
   for (int a = 0; a < 3; ++a)
     if (dims[a] == 0 || dims[a] >= (1ull << 31)) return fail(h, CUB_ERR_INVALID, "dims[%d]=%llu out of range", a, (unsigned long long)dims[a]);
-  if (direction) {
-    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
-    for (int i = 0; i < 9; ++i)
-      if (direction[i] != I[i]) return fail(h, CUB_ERR_UNSUPPORTED, "only the identity direction matrix is supported");
-  }
   for (int a = 0; a < 3; ++a) {
     const double s = spacing ? spacing[a] : 1.0;
     if (!(s > 0.0) || !std::isfinite(s)) return fail(h, CUB_ERR_INVALID, "spacing[%d] must be positive and finite", a);
     h->geom.spacing[a] = s;
     h->geom.origin[a] = origin ? origin[a] : 0.0;
     h->dims[a] = dims[a];
+  }
+  {
+    // direction cosines (itk::ImageBase::GetDirection): identity (or null) is the non-oriented image of the
+    // reference's tests; anything else switches TransformIndexToPhysicalPoint, the continuous index and the
+    // gradient to the oriented forms (cbr_common.cuh, k_project.cuh)
+    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    bool ident = true;
+    for (int i = 0; i < 9; ++i) {
+      const double d = direction ? direction[i] : I[i];
+      if (!std::isfinite(d)) return fail(h, CUB_ERR_INVALID, "direction[%d] is not finite", i);
+      ident = ident && d == I[i];
+    }
+    Geom& G = h->geom;
+    G.oriented = ident ? 0 : 1;
+    for (int k = 0; k < 9; ++k) {
+      G.dir[k] = ident ? I[k] : direction[k];
+      G.m[k] = G.dir[k] * G.spacing[k % 3];  // D * diag(spacing)
+    }
+    const double* m = G.m;  // cofactor inverse
+    const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    if (!(std::fabs(det) > 0.0) || !std::isfinite(det)) return fail(h, CUB_ERR_INVALID, "the direction matrix is singular");
+    G.minv[0] = c00 / det; G.minv[1] = (m[2] * m[7] - m[1] * m[8]) / det; G.minv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+    G.minv[3] = c01 / det; G.minv[4] = (m[0] * m[8] - m[2] * m[6]) / det; G.minv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+    G.minv[6] = c02 / det; G.minv[7] = (m[1] * m[6] - m[0] * m[7]) / det; G.minv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
   }
   h->dtype = dtype;
   h->pix_bytes = pb;
@@ -537,7 +559,8 @@ namespace {
 // slices a projected vertex can reach below / above the plane it starts on: the travel is at most the geometric sum of
 // the step lengths (max_steps + 2 moves, txx:464-469), trilinear interpolation reads one node further and the central
 // differences one more (SURVEY section 7 "projection halo")
-void projection_reach(const cub_params& P, double step_used, double spacing_z, uint64_t* below, uint64_t* above) {
+void projection_reach(const cub_params& P, double step_used, double z_index_per_unit, uint64_t* below, uint64_t* above) {
+  const double spacing_z = 1.0 / z_index_per_unit;
   const double r = P.step_relaxation, n = (double)P.max_steps + 2.0;
   double travel = (r >= 1.0) ? step_used * n : step_used * (1.0 - std::pow(r, n)) / (1.0 - r);
   if (!(travel >= 0.0)) travel = 0.0;
@@ -573,7 +596,10 @@ int count_launch(cub_handle h, const cub_params* p) {
       // a true slab: the projection must not run into the end of the local buffer (its reads would be clamped there
       // and the result would differ from the whole-image run without any error)
       uint64_t below = 0, above = 0;
-      projection_reach(*p, h->step_used, h->geom.spacing[2], &below, &above);
+      // index-space z travel per unit of physical travel: 1 / spacing_z, or the 1-norm of the z row of M^-1
+      const double zpu = h->geom.oriented ? std::fabs(h->geom.minv[6]) + std::fabs(h->geom.minv[7]) + std::fabs(h->geom.minv[8])
+                                          : 1.0 / h->geom.spacing[2];
+      projection_reach(*p, h->step_used, zpu, &below, &above);
       const uint64_t lo = h->own_z0 > below ? h->own_z0 - below : 0;
       const uint64_t hi = h->own_z1 + above < h->image_nz ? h->own_z1 + above : h->image_nz;
       if (h->local_z0 > lo || h->local_z0 + zl < hi)
@@ -611,6 +637,7 @@ int count_launch(cub_handle h, const cub_params* p) {
   CUB_TRY(ensure(h, h->seg, lattice_rows * h->NS));
   CUB_TRY(ensure(h, h->slice_any, (size_t)g.Zl + 1));
   h->raster = p->vertex_order == CUB_ORDER_RASTER;
+  CUB_TRY(ensure(h, h->cofs, entries + 4));
   if (!h->raster) CUB_TRY(ensure(h, h->own, 2 * entries));
   // entries that K2a never writes (padding columns) must read as zero counts / empty masks
   if (!had_e || layout_changed) {
@@ -656,7 +683,7 @@ int count_launch(cub_handle h, const cub_params* p) {
   {
     if (h->timing) cudaEventRecord(h->ev[6], h->stream);
     SegScanArgs sa{};
-    sa.cnt = h->cnt.p; sa.seg = h->seg.p;
+    sa.cnt = h->cnt.p; sa.seg = h->seg.p; sa.cofs = h->cofs.p;
     sa.row_begin = (unsigned)row_begin; sa.n_rows = (unsigned)n_rows;
     sa.EW = (unsigned)h->EW; sa.NS = (unsigned)h->NS;
     sa.ghost_row_end = (unsigned)((size_t)h->zs0 * h->EY);
@@ -731,12 +758,16 @@ int emit_vertex_stage(cub_handle h, bool exact) {
   const Grid& g = h->g;
   const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0;
   const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
+  const int nz = h->zs1 - h->owner_z_min;
   if (exact) {
     const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
     CUB_TRY(ensure(h, h->points, 3 * (n_pts_all + n_pts_all / 16)));
-    if (!h->raster) CUB_TRY(ensure(h, h->perm, (size_t)h->n_active + (size_t)h->n_active / 16));
+    if (!h->raster) {
+      CUB_TRY(ensure(h, h->perm, (size_t)h->n_active + (size_t)h->n_active / 16));
+      CUB_TRY(ensure(h, h->vtx, h->points.cap / 3));
+    }
     if (h->n_quads == 0) { h->vertices_done = true; return CUB_OK; }
-  } else if (!h->points.p || (!h->raster && !h->perm.p)) {
+  } else if (!h->points.p || (!h->raster && (!h->perm.p || !h->vtx.p))) {
     return kNeedSizes;
   }
   h->vertices_done = true;
@@ -744,22 +775,42 @@ int emit_vertex_stage(cub_handle h, bool exact) {
   // the points of the vertices the slab underneath owns are only needed by the projected triangle split
   const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
   if (!h->raster) {
-    VertexArgs a{};
-    a.cnt = h->cnt.p; a.act = h->act.p; a.own = h->own.p; a.seg = h->seg.p; a.info = h->d_info;
-    a.Wx = g.Wx; a.Y = g.Y; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS;
-    a.z_begin = h->owner_z_min;
-    a.plane_lo = h->zs0; a.plane_hi = h->zs1;
-    a.write_ghost_points = ghost_points ? 1 : 0;
-    a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
-    a.geom = h->geom;
-    a.points = h->points.p; a.points_cap = h->points.cap / 3;
-    a.perm = h->perm.p; a.perm_cap = h->perm.cap;
-    a.flags = h->d_info + kInfoFlags;
-    const int rows = kVertexThreads / 32;
-    const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, h->zs1 - h->owner_z_min);
-    k_vertices<<<grid, kVertexThreads, 0, h->stream>>>(a);
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
+    // the vertex kernels run over what the buffers can hold when the host does not know the counts (cub_emit_async)
+    const size_t cap = std::min(h->points.cap / 3, h->vtx.cap);
+    const size_t n_ids = exact ? (size_t)(h->ghost_v + h->n_points) : cap;
+    const unsigned n_blocks = (unsigned)((n_ids + kVertexBlockIds - 1) / kVertexBlockIds);
+    CUB_TRY(ensure(h, h->vsl, (size_t)nz + 1 + (cap + kVertexBlockIds - 1) / kVertexBlockIds + 1));
+    {
+      // K3a: vertex id -> lattice corner, walking the ownership masks K2a stored (reference creation order)
+      AssignArgs a{};
+      a.cnt = h->cnt.p; a.own = h->own.p; a.seg = h->seg.p;
+      a.Wx = g.Wx; a.Y = g.Y; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.z_begin = h->owner_z_min;
+      a.vtx = h->vtx.p; a.vtx_cap = cap; a.flags = h->d_info + kInfoFlags;
+      const int rows = kAssignThreads / 32;
+      const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, nz);
+      k_assign<<<grid, kAssignThreads, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
+    if (n_blocks > 0) {
+      // K3b: points + corner -> id map
+      SliceIndexArgs si{};
+      si.seg = h->seg.p; si.plane_segs = (size_t)h->EY * h->NS; si.z_first = h->owner_z_min; si.nz = nz;
+      si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
+      const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
+      k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
+      h->launches++;
+      VertexArgs a{};
+      a.vtx = h->vtx.p; a.info = h->d_info; a.cap = cap; a.write_ghost_points = ghost_points ? 1 : 0;
+      a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
+      a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
+      a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
+      a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
+      a.points = h->points.p; a.perm = h->perm.p; a.perm_cap = h->perm.cap; a.flags = h->d_info + kInfoFlags;
+      k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
+      h->launches++;
+      CU_TRY(h, cudaGetLastError());
+    }
   } else {
     // raster order: vertex id = corner slot, points straight from the active masks
     RasterPointArgs a{};
@@ -817,7 +868,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       FaceArgs a{};
       a.bits = h->bits.p; a.g = g; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS;
       a.z_begin = h->zs0; a.z_end = h->zs1;
-      a.act = h->act.p; a.seg = h->seg.p; a.perm = h->raster ? nullptr : h->perm.p;
+      a.act = h->act.p; a.cofs = h->cofs.p; a.seg = h->seg.p; a.perm = h->raster ? nullptr : h->perm.p;
       a.info = h->d_info;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
       a.quads_cap = quads_cap;
@@ -917,7 +968,7 @@ int cub_projection_halo(const cub_params* p, const double spacing[3], uint64_t* 
   double ms = sp[0];
   for (int a = 1; a < 3; ++a) ms = sp[a] > ms ? sp[a] : ms;
   const double step = p->step_length < 0.0 ? ms * 0.25 : p->step_length;
-  projection_reach(*p, step, sp[2], below, above);
+  projection_reach(*p, step, 1.0 / sp[2], below, above);
   return CUB_OK;
 }
 

@@ -5,11 +5,13 @@
 // (txx:279-332).  Cell ids follow voxel raster x face index (nextCellId, txx:117): cell index =
 // face base of the word + rank inside the word.  The four vertex ids of a face come from the corner -> id map:
 //     slot(corner) = slot base of the corner word + popc(act[corner word] & bits below)      id = perm[slot]
-// A warp owns one 32-word segment of a voxel row; the face base and the slot bases of the four corner rows
-// around it are the segment bases of k_seg_scan plus warp scans of the face counts / popc(act) the lanes hold
-// anyway (round 1 read them from three dense offset arrays).  The act words are loaded once per word, up front
-// together with the bitmask words (the kernel is bound by its chain of dependent loads, not by bytes).  The
-// surface voxels of a warp's 32 words are then compacted into a shared-memory queue and emitted one voxel per lane.
+// A warp owns one 32-word segment of a voxel row.  The face base of a word is the segment base of k_seg_scan plus
+// a warp scan of the face counts (it rides in the scan of the surface-voxel counts the queue needs anyway: no
+// dense face-offset array).  The slot bases of the four corner words around the word come from the dense cofs
+// array: r2 also tried to rebuild them with two more warp scans of popc(act) - fewer bytes, but 100 more
+// instructions per warp in a kernel that is bound by instruction issue (0.58 -> 0.71 ms).  All words are loaded
+// once per word, up front (the kernel is bound by its chain of dependent loads, not by bytes).  The surface
+// voxels of a warp's 32 words are then compacted into a shared-memory queue and emitted one voxel per lane.
 #pragma once
 #include "cbr_common.cuh"
 #include "k_segscan.cuh"
@@ -24,6 +26,7 @@ struct FaceArgs {
   int EY, EW, NS;
   int z_begin, z_end;          // local voxel slices whose faces are emitted (the handle's own range)
   const uint32_t* act;
+  const uint32_t* cofs;        // entry lattice, exclusive scan of the active-corner counts (slot bases)
   const uint4* seg;            // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   const uint32_t* perm;        // slot -> scan-relative vertex id
   const unsigned long long* info;  // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
@@ -126,21 +129,17 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
 
   // ---- face masks of the word (txx:164-173; clamped neighbours: no face on the image border) --------------
   uint32_t F[6] = {0, 0, 0, 0, 0, 0};
-  // context of the word: active masks of the 4 corner words around it (index oz*2+oy) and the segment bases of
-  // their rows {-, faces, active corners, -}
+  // context of the word: active masks and slot bases of the 4 corner words around it (index oz*2+oy), the
+  // segment base of its row {-, faces, -, -}
   const int plane = a.EY * a.EW;                           // entries per plane (< 2^31)
   const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
-  uint32_t A[4] = {0, 0, 0, 0};
-  uint4 sb[4] = {};
+  uint32_t A[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0};
+  uint32_t fseg = 0;
   {
     // all the words are requested together (no early-out on an empty word: that would make the neighbour
     // loads wait for the first one, and the kernel is bound by its chain of dependent loads)
     const bool valid = w < g.Wx && y < g.Y;
-    if (y < g.Y) {
-      const size_t r0 = (size_t)zl * a.EY + y;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) sb[k] = __ldg(a.seg + (r0 + (size_t)(k >> 1) * a.EY + (k & 1)) * a.NS + sgm);
-    }
+    if (y < g.Y) fseg = __ldg(&a.seg[((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.NS + (uint32_t)sgm].y);
     // word and entry indices fit 32 bits (cub_count checks the lattice size): one IMAD.WIDE per load
     const uint32_t* __restrict__ row = a.bits + (((uint32_t)zl * (uint32_t)g.Y + (uint32_t)y) * (uint32_t)g.Wp + (uint32_t)w);
     const int zgl = zl + g.zg0;
@@ -151,7 +150,11 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     uint32_t c0 = 0, nym = 0, nyp = 0, nzm = 0, nzp = 0, edge = 0;
     if (valid) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) A[k] = __ldg(a.act + e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW));
+      for (int k = 0; k < 4; ++k) {
+        const uint32_t e = e00 + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW);
+        A[k] = __ldg(a.act + e);
+        C[k] = __ldg(a.cofs + e);
+      }
       c0 = __ldg(row);
       nym = __ldg(row + dym); nyp = __ldg(row + dyp); nzm = __ldg(row + dzm); nzp = __ldg(row + dzp);
       // the x neighbours are the adjacent lanes' words, except across the ends of the warp's 32-word segment
@@ -176,15 +179,13 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   uint32_t U = F[0] | F[1] | F[2] | F[3] | F[4] | F[5];
   const uint32_t nvox = __popc(U);
   const uint32_t nf = __popc(F[0]) + __popc(F[1]) + __popc(F[2]) + __popc(F[3]) + __popc(F[4]) + __popc(F[5]);
-  // warp scans in 16-bit fields: surface voxels (queue positions) | faces (cell ids); active corners of the
-  // four corner rows (slots)
+  // one warp scan in two 16-bit fields: surface voxels (queue positions) | faces (cell ids)
   uint32_t s0 = nvox | (nf << 16);
-  uint32_t s1 = (uint32_t)__popc(A[0]) | ((uint32_t)__popc(A[1]) << 16), s2 = (uint32_t)__popc(A[2]) | ((uint32_t)__popc(A[3]) << 16);
-  const uint32_t m0 = s0, m1 = s1, m2 = s2;
+  const uint32_t m0 = s0;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
-    if (lane >= o) { s0 += t0; s1 += t1; s2 += t2; }
+    const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o);
+    if (lane >= o) s0 += t0;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, s0, 31) & 0xffffu;
   if (total == 0) return;  // no surface voxel in the 1024 voxels of the segment
@@ -192,12 +193,12 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   const uint32_t ghost_f = (uint32_t)__ldg(a.info + kInfoMarkF);
 
   if (U) {
-    s0 -= m0; s1 -= m1; s2 -= m2;  // exclusive
+    s0 -= m0;  // exclusive
     uint4* cx = sm.ctx[warp][lane];
     cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
-    cx[1] = make_uint4(sb[0].z + (s1 & 0xffffu), sb[1].z + (s1 >> 16), sb[2].z + (s2 & 0xffffu), sb[3].z + (s2 >> 16));
+    cx[1] = make_uint4(C[0], C[1], C[2], C[3]);
     cx[2] = make_uint4(F[0], F[1], F[2], F[3]);
-    cx[3] = make_uint4(F[4], F[5], sb[0].y + (s0 >> 16) - ghost_f, 0u);
+    cx[3] = make_uint4(F[4], F[5], fseg + (s0 >> 16) - ghost_f, 0u);
     uint32_t pos = s0 & 0xffffu;
     uint16_t* q = sm.queue[warp];
     const uint32_t tag = (uint32_t)lane << 5;

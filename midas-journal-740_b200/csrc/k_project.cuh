@@ -84,6 +84,20 @@ __device__ __forceinline__ void gradient_at(const VolView<T>& v, const float c[3
   }
 }
 
+// GradientImageFilter::m_UseImageDirection on an oriented image: every gradient pixel is rotated into physical space,
+// TransformLocalVectorToPhysicalVector: fp64 row sums (from 0) of D * fp32 gradient, rounded to fp32
+__device__ __forceinline__ void rotate_gradient(const Geom& geom, float g[3]) {
+  float r[3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    double sum = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) sum += geom.dir[3 * i + j] * (double)g[j];
+    r[i] = (float)sum;
+  }
+  g[0] = r[0]; g[1] = r[1]; g[2] = r[2];
+}
+
 __device__ __forceinline__ int clampi(long long v, int hi) { return v < 0 ? 0 : (v > hi ? hi : (int)v); }
 
 // Persistent lanes: the number of moves varies from 0 to max_steps+2 between vertices, so a lane that finishes
@@ -133,12 +147,30 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     // continuous index, base index and distances (shared by both interpolators)
     long long base[3];
     double dist[3];
+    {
+      double ci[3];
+      if (!a.geom.oriented) {
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double ci = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
-      const double f = floor(ci);
-      base[k] = (long long)f - a.i0[k];  // buffer-relative
-      dist[k] = ci - f;
+        for (int k = 0; k < 3; ++k) ci[k] = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
+      } else {
+        // TransformPhysicalPointToContinuousIndex of an oriented image: M^-1 * (point - origin), row sums from 0
+        double c[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) c[k] = (double)vert[k] - a.geom.origin[k];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+          double sum = 0.0;
+#pragma unroll
+          for (int j = 0; j < 3; ++j) sum += a.geom.minv[3 * i + j] * c[j];
+          ci[i] = sum;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double f = floor(ci[k]);
+        base[k] = (long long)f - a.i0[k];  // buffer-relative
+        dist[k] = ci[k] - f;
+      }
     }
     if (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2]) {
       cell[0] = base[0]; cell[1] = base[1]; cell[2] = base[2];
@@ -191,6 +223,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           { float s = 0.0f; s += (-gc[0]) * xm; s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
           { float s = 0.0f; s += (-gc[1]) * ym; s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
           { float s = 0.0f; s += (-gc[2]) * zm; s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
+          if (a.geom.oriented) rotate_gradient(a.geom, ngrad[counter]);
         }
       } else {
 #pragma unroll 1
@@ -200,6 +233,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
           float gtmp[3];
           gradient_at(v, gc, cx, cy, cz, gtmp);
+          if (a.geom.oriented) rotate_gradient(a.geom, gtmp);
           const double nv = (double)v.at(cx, cy, cz);
           // (dynamic index into the register cache: written through a switch so that it stays in registers)
 #pragma unroll

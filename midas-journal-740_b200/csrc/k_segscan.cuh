@@ -13,13 +13,15 @@
 // "one warp = 32 consecutive entries of a lattice row", so all it needs is the prefix at the START of its
 // segment: the rest is a warp shuffle scan of counts it has in registers anyway.  This kernel therefore writes
 // one uint4 {vertices, faces, active corners, -} per 32-entry segment of a row (NS = ceil(EW/32) segments per
-// row): 4 B in, 16/32 B out per entry.
+// row), plus ONE dense array, the active-corner prefix cofs (the slot bases): it is gathered per VERTEX by
+// k_vertices, which has no warp-per-row structure to scan in, and rebuilding it in k_faces with two more warp
+// scans cost more issue slots than the four loads (measured in r2).  4 B in, 4.5 B out per entry.
 //
 // Structure: one large tile (whole lattice rows) per resident CTA, chained with decoupled look-back (flag +
 // value in one 64-bit descriptor per tile and quantity, tiles handed out by an atomic ticket so that a tile
 // only ever waits for tiles that started before it).  Inside a tile every warp owns a contiguous run of rows:
 //   pass 1  the warp sums its rows (coalesced 16-byte loads)  -> CTA aggregate -> look-back -> tile prefix
-//   pass 2  the warp walks its rows again (L1/L2), one warp reduction per segment, and writes the segment bases.
+//   pass 2  the warp walks its rows again (L1/L2), one lane per row, 32 rows at a time, and writes the segment bases.
 #pragma once
 #include <climits>
 
@@ -54,6 +56,7 @@ enum { kFlagBufferOverflow = 1, kFlagEmptyInteriorSlice = 2, kFlagIdOverflow = 4
 struct SegScanArgs {
   const uint32_t* cnt;
   uint4* seg;                    // [rows of the lattice][NS] exclusive prefixes at the start of every segment
+  uint32_t* cofs;                // entry lattice: dense exclusive prefix of the active-corner counts, or null
   unsigned row_begin, n_rows;    // scanned lattice rows [row_begin, row_begin + n_rows): whole planes
   unsigned EW, NS;               // entries / segments per row
   unsigned ghost_row_end;        // active corners of rows below this one belong to the slab underneath: not counted
@@ -159,25 +162,58 @@ __global__ void __launch_bounds__(kScanThreads) k_seg_scan(const SegScanArgs a) 
   unsigned long long run_v = s_excl[0], run_f = s_excl[1], run_c = s_excl[2];
   for (int i = 0; i < warp; ++i) { run_v += s_part[0][i]; run_f += s_part[1][i]; run_c += s_part[2][i]; }
 
-  // ---- pass 2: segment bases ------------------------------------------------------------------------------
+  // ---- pass 2: segment bases.  One lane per row, 32 rows of the warp's run at a time: the lane sums its row
+  // (all loads independent), a warp scan over the 32 rows gives every row's prefix, and the lane walks its row
+  // once more (L1) to write the prefix at the start of every 32-entry segment. ------------------------------
   uint32_t v = (uint32_t)run_v, f = (uint32_t)run_f, c = (uint32_t)run_c;  // (a handle's totals fit 32 bits: cub_count checks)
-  for (unsigned r = r0; r < r1; ++r) {
-    const unsigned row = a.row_begin + r;
-    const uint32_t* __restrict__ p = a.cnt + (size_t)row * a.EW;
+  const unsigned ew4 = a.EW / 4;
+  for (unsigned rb = r0; rb < r1; rb += 32) {
+    const unsigned r = rb + lane;
+    const bool live = r < r1;
+    const unsigned row = a.row_begin + (live ? r : r1 - 1);
+    const uint4* __restrict__ p = reinterpret_cast<const uint4*>(a.cnt + (size_t)row * a.EW);
     const bool counted = row >= a.ghost_row_end;
-    if (lane == 0) {
-      if (row == a.mark_row_vf) { a.info[kInfoMarkV] = v; a.info[kInfoMarkF] = f; }
-      if (row == a.mark_row_c) a.info[kInfoMarkC] = c;
+    uint32_t tv = 0, tf = 0, tc = 0;
+    if (live) {
+      for (unsigned k = 0; k < ew4; ++k) {
+        const uint4 q = __ldg(p + k);
+        tv += (q.x & 0x3ffu) + (q.y & 0x3ffu) + (q.z & 0x3ffu) + (q.w & 0x3ffu);
+        tf += ((q.x >> 10) & 0x3ffu) + ((q.y >> 10) & 0x3ffu) + ((q.z >> 10) & 0x3ffu) + ((q.w >> 10) & 0x3ffu);
+        tc += (q.x >> 20) + (q.y >> 20) + (q.z >> 20) + (q.w >> 20);
+      }
+      if (!counted) tc = 0;
     }
-    for (unsigned s = 0; s < a.NS; ++s) {
-      const unsigned w = s * 32 + lane;
-      const uint32_t q = w < a.EW ? __ldg(p + w) : 0u;
-      if (lane == 0) a.seg[(size_t)row * a.NS + s] = make_uint4(v, f, c, 0u);
-      v += __reduce_add_sync(0xffffffffu, q & 0x3ffu);
-      f += __reduce_add_sync(0xffffffffu, (q >> 10) & 0x3ffu);
-      const uint32_t qc = __reduce_add_sync(0xffffffffu, q >> 20);
-      if (counted) c += qc;
+    uint32_t iv = tv, jf = tf, ic = tc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, iv, o), y = __shfl_up_sync(0xffffffffu, jf, o), z = __shfl_up_sync(0xffffffffu, ic, o);
+      if (lane >= o) { iv += x; jf += y; ic += z; }
     }
+    if (live) {
+      uint32_t bv = v + iv - tv, bf = f + jf - tf, bc = c + ic - tc;  // prefix at the start of the lane's row
+      if (row == a.mark_row_vf) { a.info[kInfoMarkV] = bv; a.info[kInfoMarkF] = bf; }
+      if (row == a.mark_row_c) a.info[kInfoMarkC] = bc;
+      uint4* __restrict__ out = a.seg + (size_t)row * a.NS;
+      uint4* __restrict__ co = a.cofs ? reinterpret_cast<uint4*>(a.cofs + (size_t)row * a.EW) : nullptr;
+      for (unsigned k = 0; k < ew4; ++k) {
+        if ((k & 7u) == 0) out[k >> 3] = make_uint4(bv, bf, bc, 0u);   // segment k / 8 starts at entry 4 k
+        const uint4 q = __ldg(p + k);
+        bv += (q.x & 0x3ffu) + (q.y & 0x3ffu) + (q.z & 0x3ffu) + (q.w & 0x3ffu);
+        bf += ((q.x >> 10) & 0x3ffu) + ((q.y >> 10) & 0x3ffu) + ((q.z >> 10) & 0x3ffu) + ((q.w >> 10) & 0x3ffu);
+        if (co) {
+          // the dense slot bases (exclusive prefix of the active-corner counts): k_vertices gathers them per vertex,
+          // k_faces loads them per word
+          uint4 o;
+          const uint32_t m = counted ? 0xffffffffu : 0u;
+          o.x = bc; o.y = o.x + ((q.x >> 20) & m); o.z = o.y + ((q.y >> 20) & m); o.w = o.z + ((q.z >> 20) & m);
+          bc = o.w + ((q.w >> 20) & m);
+          co[k] = o;
+        } else if (counted) {
+          bc += (q.x >> 20) + (q.y >> 20) + (q.z >> 20) + (q.w >> 20);
+        }
+      }
+    }
+    v += __shfl_sync(0xffffffffu, iv, 31); f += __shfl_sync(0xffffffffu, jf, 31); c += __shfl_sync(0xffffffffu, ic, 31);
   }
 }
 

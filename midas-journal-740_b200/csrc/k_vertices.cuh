@@ -1,21 +1,24 @@
-// k_vertices.cuh — K3a: vertex creation.  One warp per 32-word segment of a voxel row walks the ownership masks
-// K2a stored and emits, for every owned corner, its point and its entry of the corner -> vertex-id map.
+// k_vertices.cuh — K3a / K3b: vertex creation in the reference's order.
 //
 // Reference: the vertex creation loop txx:179-194 (voxels in raster order, local corners 0..7, a corner gets
 // nextVertexId the first time it is touched) and AddVertex without the projection (txx:257-276):
 // TransformIndexToPhysicalPoint, minus half a spacing, mesh->GetPoints()->InsertElement(id, vertex).
 //
-// Round 1 did this in three kernels (k_assign: one thread per word walking its masks and writing 4-byte records
-// in id order; k_slice_index; k_vertices: one thread per record -> point + map entry: 0.48 ms, 2.4 GB of DRAM
-// traffic for 44 M vertices).  Here the ids of a segment are consecutive (segment base from k_seg_scan + a
-// warp scan of the words' counts), so the warp
-//   1. walks the masks of its 32 words (voxel bit, then local corner 0..7: the reference's creation order
-//      inside the word) into a shared-memory queue of (word, bit, local corner) items - queue position = id, and
-//   2. handles one item per lane: the point (consecutive lanes write consecutive ids: coalesced) and
-//          perm[slot(corner)] = id,   slot(corner) = cseg[corner row segment] + popc(active corners before it),
-//      which is where the face kernel looks the id up.  The active-corner prefix inside the segment is a warp
-//      scan of popc(act) of the four corner rows around the voxel row.
-// No per-vertex record array, no slice bisection, no gather of dense offset arrays.
+//   K3a k_assign   one warp per 32-word segment of a voxel row.  K2a (k_sweep.cuh) decided, per voxel word, which
+//                  voxel owns which of its 8 local corners (8 masks, stored where the word owns anything); the
+//                  first id of a word is the segment base of k_seg_scan plus a warp scan of the words' counts.
+//                  Lanes whose word owns a corner walk the masks - voxels in bit order, local corners 0..7 - and
+//                  record for vertex id (first id + rank) the corner it sits on: cx | cy << 16 | oz << 31.
+//   K3b k_vertices one thread per vertex id, perfectly balanced and coalesced: reads the 4-byte record, writes the
+//                  12-byte point and stores its id at the corner's rank in corner-raster order,
+//                      perm[cofs[corner word] + popc(act[corner word] & bits below)] = id,
+//                  which is where the face kernel looks it up.  The owner slice of an id follows from the
+//                  per-slice first ids (ids are handed out slice by slice; k_slice_index).
+//
+// r2 also tried ONE kernel for both (a warp walks the masks into a shared queue and then emits one vertex per
+// lane, slots from warp scans of popc(act) of the four corner rows: no record array, no dense cofs): 0.75 ms
+// against 0.48 ms for this pair - every warp then pays the corner context of all its 32 words, while k_assign
+// drops the 57 % of words that own nothing after one load and k_vertices has no per-word work at all.
 //
 // In raster vertex order (the opt-in canonical order) ids ARE slots and k_points_raster writes the points
 // straight from the active masks.
@@ -25,134 +28,163 @@
 
 namespace cbr {
 
-struct VertexArgs {
-  const uint32_t* cnt;      // entry lattice: owned corners in the low 10 bits
-  const uint32_t* act;      // entry lattice: active-corner masks
-  const uint4* own;         // entry lattice x 2: ownership masks O[0..3], O[4..7] (valid where the word owns a corner)
-  const uint4* seg;         // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
-  const unsigned long long* info;
+struct AssignArgs {
+  const uint32_t* cnt;    // entry lattice: owned corners in the low 10 bits
+  const uint4* own;       // entry lattice x 2: ownership masks O[0..3], O[4..7]
+  const uint4* seg;       // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   int Wx, Y, EY, EW, NS;
-  int z_begin;              // first local slice of the scan range (blockIdx.z = 0)
-  int plane_lo, plane_hi;   // local corner planes that faces of this handle reference (inclusive)
+  int z_begin;            // first local slice of the scan range (blockIdx.z = 0)
+  uint32_t* vtx;          // [n vertices] cx | cy << 16 | oz << 31
+  size_t vtx_cap;
+  unsigned long long* flags;
+};
+
+constexpr int kAssignThreads = 128;  // (one row segment per warp)
+
+__global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
+  // grid: x = 32-word segments of a row, y = groups of kAssignThreads / 32 rows (one row per warp), z = slices of the scan range
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
+  if (y >= a.Y) return;  // (warp-uniform)
+  const uint32_t row = (uint32_t)z * (uint32_t)a.EY + (uint32_t)y;
+  const uint32_t e = row * (uint32_t)a.EW + (uint32_t)w;
+  const uint32_t nv = w < a.Wx ? (__ldg(a.cnt + e) & 0x3ffu) : 0u;
+  // first id of the word: segment base + exclusive warp scan of the owned-corner counts
+  uint32_t incl = nv;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (nv == 0) return;
+  uint32_t n = __ldg(&a.seg[row * (uint32_t)a.NS + blockIdx.x].x) + incl - nv;
+  if ((size_t)n + nv > a.vtx_cap) { atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow); return; }
+  const uint4 lo = __ldcs(a.own + 2 * (size_t)e), hi = __ldcs(a.own + 2 * (size_t)e + 1);
+  const uint32_t O[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+  uint32_t U = O[0] | O[1] | O[2] | O[3] | O[4] | O[5] | O[6] | O[7];
+  uint32_t* __restrict__ const out = a.vtx;
+  const uint32_t xy0 = (uint32_t)(w * 32) | ((uint32_t)y << 16);
+  while (U) {
+    const int b = __ffs(U) - 1;
+    U &= U - 1;
+    const uint32_t bit = 1u << b;
+    const uint32_t xy = xy0 + (uint32_t)b;
+    // local corner l -> (ox, oy, oz) as in txx:236-254; a 32-bit running index (a predicated 64-bit pointer bump
+    // costs 6 instructions per store)
+    if (O[0] & bit) { out[n] = xy; ++n; }
+    if (O[1] & bit) { out[n] = xy + 1u; ++n; }
+    if (O[2] & bit) { out[n] = xy + 0x10001u; ++n; }
+    if (O[3] & bit) { out[n] = xy + 0x10000u; ++n; }
+    if (O[4] & bit) { out[n] = xy + 0x80000000u; ++n; }
+    if (O[5] & bit) { out[n] = xy + 0x80000001u; ++n; }
+    if (O[6] & bit) { out[n] = xy + 0x80010001u; ++n; }
+    if (O[7] & bit) { out[n] = xy + 0x80010000u; ++n; }
+  }
+}
+
+struct VertexArgs {
+  const uint32_t* vtx;      // [n] packed corner of vertex id (scan-relative id): cx | cy << 16 | oz << 31
+  const uint32_t* slice_first;  // [nz + 1] first id created by slice z_first + k; [nz] = UINT_MAX   (k_slice_index)
+  const uint32_t* block_slice;  // [blocks of this launch] k of the block's first id                  (k_slice_index)
+  const unsigned long long* info;  // kInfoTotV: ghost vertices + own vertices; kInfoGhostV
+  int z_first;              // first local slice of the scan range
+  size_t cap;               // vertices the record / point buffers can hold
   int write_ghost_points;   // also write the points of the vertices that belong to the slab underneath
+  const uint32_t* act;      // entry lattice [Zl+1][EY][EW]
+  const uint32_t* cofs;
+  int EY, EW;
+  int plane_lo, plane_hi;   // local corner planes that faces of this handle reference (inclusive)
   int coff[3];              // image index of lattice corner (0, 0, 0): slab offset, region index, minus the pad of image_border_faces
   Geom geom;
   float* points;            // indexed by scan-relative vertex id
-  size_t points_cap;        // points the buffer can hold
   uint32_t* perm;           // [active corners of planes plane_lo..plane_hi] -> scan-relative vertex id
   size_t perm_cap;
-  unsigned long long* flags;  // info + kInfoFlags
+  unsigned long long* flags;
 };
 
-constexpr int kVertexThreads = 128;   // one voxel row segment per warp
-constexpr int kVertexQueue = 512;     // items per warp and pass
-
-struct VertexSmem {
-  uint32_t A[kVertexThreads / 32][32][4];   // active masks of the 4 corner words around the voxel word (index oz*2+oy)
-  uint32_t C[kVertexThreads / 32][32][4];   // their slots bases
-  uint16_t queue[kVertexThreads / 32][kVertexQueue];  // word << 8 | bit << 3 | local corner
+// ids are handed out slice by slice, so the owner slice of an id follows from the per-slice first ids: this
+// one-off kernel reads them out of the segment bases (the base of the first segment of a plane's first row) and
+// bisects once per k_vertices block, so that the vertex threads only step forward from their block's slice
+// (almost always zero steps).
+struct SliceIndexArgs {
+  const uint4* seg;
+  size_t plane_segs;        // EY * NS: segments per plane
+  int z_first, nz;          // local slices [z_first, z_first + nz) of the scan range
+  uint32_t* slice_first;    // [nz + 1]
+  uint32_t* block_slice;    // [n_blocks]
+  uint32_t n_blocks, ids_per_block;
 };
 
-__global__ void __launch_bounds__(kVertexThreads) k_vertices(const VertexArgs a) {
-  __shared__ VertexSmem sm;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int sgm = blockIdx.x, w = sgm * 32 + lane, y = blockIdx.y * (kVertexThreads / 32) + warp, z = a.z_begin + blockIdx.z;
-  const bool valid = w < a.Wx && y < a.Y;
-  const int plane = a.EY * a.EW;
-  const uint32_t e = ((uint32_t)z * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;
-  // everything is requested up front
-  uint32_t nv = 0, A[4] = {0, 0, 0, 0};
-  uint4 sb[4] = {};
-  if (y < a.Y) {
-    const size_t r0 = (size_t)z * a.EY + y;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) sb[k] = __ldg(a.seg + (r0 + (size_t)(k >> 1) * a.EY + (k & 1)) * a.NS + sgm);
+__global__ void __launch_bounds__(256) k_slice_index(const SliceIndexArgs a) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t <= (uint32_t)a.nz) a.slice_first[t] = t < (uint32_t)a.nz ? __ldg(&a.seg[(size_t)(a.z_first + t) * a.plane_segs].x) : 0xffffffffu;
+  if (t >= a.n_blocks) return;
+  const uint32_t id = t * a.ids_per_block;
+  int lo = 0, hi = a.nz - 1;  // largest k with first[k] <= id
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (__ldg(&a.seg[(size_t)(a.z_first + mid) * a.plane_segs].x) <= id) lo = mid; else hi = mid - 1;
   }
-  if (valid) {
-    nv = __ldg(a.cnt + e) & 0x3ffu;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) A[k] = __ldg(a.act + e + (uint32_t)((k >> 1) * plane + (k & 1) * a.EW));
-  }
-  // warp scans: owned corners (ids) and active corners of the four corner rows (slots), 16-bit fields
-  uint32_t s0 = nv, s1 = (uint32_t)__popc(A[0]) | ((uint32_t)__popc(A[1]) << 16), s2 = (uint32_t)__popc(A[2]) | ((uint32_t)__popc(A[3]) << 16);
-  const uint32_t m0 = s0, m1 = s1, m2 = s2;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t t0 = __shfl_up_sync(0xffffffffu, s0, o), t1 = __shfl_up_sync(0xffffffffu, s1, o), t2 = __shfl_up_sync(0xffffffffu, s2, o);
-    if (lane >= o) { s0 += t0; s1 += t1; s2 += t2; }
-  }
-  const uint32_t total = __shfl_sync(0xffffffffu, s0, 31);
-  if (total == 0) return;  // no corner is owned by the 1024 voxels of the segment
-  const uint32_t first = s0 - m0;  // position of the lane's first item
-  s1 -= m1; s2 -= m2;
-  if (nv) {
-    uint32_t* cA = sm.A[warp][lane];
-    uint32_t* cC = sm.C[warp][lane];
-    cA[0] = A[0]; cA[1] = A[1]; cA[2] = A[2]; cA[3] = A[3];
-    cC[0] = sb[0].z + (s1 & 0xffffu); cC[1] = sb[1].z + (s1 >> 16); cC[2] = sb[2].z + (s2 & 0xffffu); cC[3] = sb[3].z + (s2 >> 16);
-  }
-  uint32_t O[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (nv) {
-    const uint4 lo = __ldcs(a.own + 2 * (size_t)e), hi = __ldcs(a.own + 2 * (size_t)e + 1);
-    O[0] = lo.x; O[1] = lo.y; O[2] = lo.z; O[3] = lo.w; O[4] = hi.x; O[5] = hi.y; O[6] = hi.z; O[7] = hi.w;
-  }
-  const uint32_t Uall = O[0] | O[1] | O[2] | O[3] | O[4] | O[5] | O[6] | O[7];
-  const uint32_t vbase = sb[0].x;                                   // first id of the segment (scan-relative)
-  const unsigned long long first_point = a.write_ghost_points ? 0ull : __ldg(a.info + kInfoGhostV);
-  uint16_t* q = sm.queue[warp];
+  a.block_slice[t] = (uint32_t)lo;
+}
 
-  for (uint32_t base = 0; base < total; base += kVertexQueue) {
-    // ---- 1. the lanes whose items fall into [base, base + kVertexQueue) walk their masks ------------------
-    if (nv && first < base + kVertexQueue && first + nv > base) {
-      uint32_t U = Uall, pos = first;
-      const uint32_t tag = (uint32_t)lane << 8;
-      while (U) {
-        const int b = __ffs(U) - 1;
-        U &= U - 1;
-        // local corners of voxel b that it owns, as a byte (bit l <-> local corner l, txx:179-194 creation order)
-        uint32_t m = 0;
+constexpr int kVertexPerThread = 4;                       // ids per thread: the loads of the 4 are in flight together
+constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a chain of 3 dependent loads otherwise)
+
+__global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
+  // the number of vertices comes from the device-side run info (the grid may be sized for the buffer's capacity)
+  const size_t n_all = (size_t)__ldg(a.info + kInfoTotV);
+  const size_t n = n_all < a.cap ? n_all : a.cap;
+  const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
+  if ((size_t)blockIdx.x * kVertexBlockIds >= n) {
+    if (n_all > a.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
+    return;
+  }
+  const size_t first_point = a.write_ghost_points ? 0 : (size_t)__ldg(a.info + kInfoGhostV);
+  uint32_t v[kVertexPerThread];
 #pragma unroll
-        for (int l = 0; l < 8; ++l) m |= ((O[l] >> b) & 1u) << l;
-        while (m) {
-          const int l = __ffs(m) - 1;
-          m &= m - 1;
-          const uint32_t rel = pos - base;   // (wraps for items before the window)
-          if (rel < (uint32_t)kVertexQueue) q[rel] = (uint16_t)(tag | ((uint32_t)b << 3) | (uint32_t)l);
-          ++pos;
-        }
-      }
+  for (int j = 0; j < kVertexPerThread; ++j) {
+    const size_t id = id0 + (size_t)j * 256;
+    v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
+  }
+  int lo = (int)__ldg(a.block_slice + blockIdx.x);
+  int cz[kVertexPerThread];
+#pragma unroll
+  for (int j = 0; j < kVertexPerThread; ++j) {
+    const size_t id = id0 + (size_t)j * 256;
+    if (id < n)
+      while ((uint32_t)id >= __ldg(a.slice_first + lo + 1)) ++lo;
+    cz[j] = a.z_first + lo + (int)(v[j] >> 31);
+  }
+  uint32_t co[kVertexPerThread], ac[kVertexPerThread];
+#pragma unroll
+  for (int j = 0; j < kVertexPerThread; ++j) {
+    const size_t id = id0 + (size_t)j * 256;
+    const int cx = (int)(v[j] & 0xffffu), cy = (int)((v[j] >> 16) & 0x7fffu);
+    co[j] = ac[j] = 0;
+    if (id < n && cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
+      const size_t e = ((size_t)cz[j] * a.EY + cy) * a.EW + (cx >> 5);
+      co[j] = __ldg(a.cofs + e);
+      ac[j] = __ldg(a.act + e);
     }
-    __syncwarp();
-    // ---- 2. one item per lane -----------------------------------------------------------------------------
-    const uint32_t end = min(total - base, (uint32_t)kVertexQueue);
-    for (uint32_t s = lane; s < end; s += 32) {
-      const uint32_t it = q[s];
-      const uint32_t src = it >> 8, b = (it >> 3) & 31u, l = it & 7u;
-      // local corner l -> (ox, oy, oz) as in txx:236-254: 0(0,0,0) 1(1,0,0) 2(1,1,0) 3(0,1,0) 4(0,0,1) 5(1,0,1) 6(1,1,1) 7(0,1,1)
-      const uint32_t ox = (l ^ (l >> 1)) & 1u, oy = (l >> 1) & 1u, oz = l >> 2;
-      const uint32_t k = oz * 2 + oy;
-      const uint32_t cb = b + ox;  // corner bit inside corner word `src` (32: bit 0 of the next word)
-      const uint32_t Ak = sm.A[warp][src][k], Ck = sm.C[warp][src][k];
-      const uint32_t below = cb >= 32u ? 0xffffffffu : ((1u << cb) - 1u);
-      const uint32_t slot = Ck + (uint32_t)__popc(Ak & below);
-      const unsigned long long id = (unsigned long long)vbase + base + s;  // scan-relative vertex id
-      const int cx = (sgm * 32 + (int)src) * 32 + (int)cb, cy = y + (int)oy, cz = z + (int)oz;
-      if (id >= first_point) {
-        if (id < a.points_cap) {
-          float* p = a.points + 3 * id;
-          p[0] = corner_coord(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-          p[1] = corner_coord(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-          p[2] = corner_coord(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-        } else {
-          atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
-        }
-      }
-      if (cz >= a.plane_lo && cz <= a.plane_hi) {
-        if (slot < a.perm_cap) a.perm[slot] = (uint32_t)id;
-        else atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
-      }
+  }
+#pragma unroll
+  for (int j = 0; j < kVertexPerThread; ++j) {
+    const size_t id = id0 + (size_t)j * 256;
+    if (id >= n) break;
+    const int cx = (int)(v[j] & 0xffffu), cy = (int)((v[j] >> 16) & 0x7fffu);
+    if (id >= first_point) {
+      float* p = a.points + 3 * id;
+      p[0] = corner_coord(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
+      p[1] = corner_coord(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
+      p[2] = corner_coord(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
     }
-    __syncwarp();
+    if (cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
+      const uint32_t below = (1u << (cx & 31)) - 1u;
+      const uint32_t slot = co[j] + __popc(ac[j] & below);
+      if (slot < a.perm_cap) a.perm[slot] = (uint32_t)id;
+      else atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
+    }
   }
 }
 

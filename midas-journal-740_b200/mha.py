@@ -25,7 +25,7 @@ class Image:
     data: np.ndarray
     spacing: tuple = (1.0, 1.0, 1.0)
     origin: tuple = (0.0, 0.0, 0.0)
-    direction: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    direction: tuple = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)   # itk direction cosines, row-major D[i][j]
     meta: dict = field(default_factory=dict)
     region_index: tuple = (0, 0, 0)   # itk::ImageRegion::GetIndex of the buffered region (x, y, z)
 
@@ -60,7 +60,10 @@ def read_mha(path: str) -> Image:
     data = np.frombuffer(payload, dtype=dtype, count=nx * ny * nz).reshape(nz, ny, nx).copy()
     spacing = tuple(float(v) for v in meta.get("ElementSpacing", "1 1 1").split())
     origin = tuple(float(v) for v in meta.get("Offset", meta.get("Position", "0 0 0")).split())
-    direction = tuple(float(v) for v in meta.get("TransformMatrix", "1 0 0 0 1 0 0 0 1").split())
+    # MetaImage lists the axis direction vectors one after the other, i.e. the COLUMNS of itk's direction
+    # matrix (MetaImageIO: TransformMatrix(i, j) = direction[j][i]); Image.direction is row-major D[i][j]
+    tm = [float(v) for v in meta.get("TransformMatrix", "1 0 0 0 1 0 0 0 1").split()]
+    direction = tuple(tm[3 * j + i] for i in range(3) for j in range(3))
     return Image(data, spacing, origin, direction, meta)
 
 
@@ -75,11 +78,11 @@ def write_mha(path: str, img: Image, compress: bool = True) -> None:
     else:
         lines += ["CompressedData = False"]
     lines += [
-        "TransformMatrix = " + " ".join(f"{v:g}" for v in img.direction),
-        "Offset = " + " ".join(f"{v:g}" for v in img.origin),
+        "TransformMatrix = " + " ".join(f"{float(img.direction[3 * j + i])!r}" for i in range(3) for j in range(3)),
+        "Offset = " + " ".join(f"{float(v)!r}" for v in img.origin),
         "CenterOfRotation = 0 0 0",
         "AnatomicalOrientation = RAI",
-        "ElementSpacing = " + " ".join(f"{v:g}" for v in img.spacing),
+        "ElementSpacing = " + " ".join(f"{float(v)!r}" for v in img.spacing),
         f"DimSize = {nx} {ny} {nz}",
         f"ElementType = {_MET_NAMES[data.dtype]}",
         "ElementDataFile = LOCAL",

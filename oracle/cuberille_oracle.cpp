@@ -26,6 +26,14 @@
 //   * GradientImageFilter: fp32 central differences, edge replicate (txx:486-495).
 //   * CovariantVector<float,3>::Normalize (txx:452).
 //   * Point::SquaredEuclideanDistanceTo (txx:298).
+//   * Oriented images (a non-identity direction matrix D; no test of the reference has one):
+//     itk::Image::TransformIndexToPhysicalPoint with M = D*diag(spacing) into a Point<float> (every
+//     accumulation rounds to float), TransformPhysicalPointToContinuousIndex with M^-1 (fp64, row sums from 0),
+//     GradientImageFilter's UseImageDirection rotation of every gradient pixel
+//     (TransformLocalVectorToPhysicalVector: fp64 row sums of D * fp32 gradient, rounded to fp32).  The
+//     reference's half-spacing shift stays axis-aligned in PHYSICAL space (txx:268-270), as written.
+//     M^-1 is the cofactor inverse here (ITK takes vnl's SVD inverse: equal for axis flips / permutations,
+//     equal to rounding otherwise).
 //
 // Build: see oracle/Makefile (g++ -O2 -ffp-contract=off; no -ffast-math, no -march).
 
@@ -61,6 +69,7 @@ struct orc_params {
                                 // 1: a neighbour outside the image is outside the surface (closed mesh, txx:133 TODO)
   int64_t region_index[3];      // image index of the buffer's first voxel (ImageRegion::GetIndex; the tests of the
                                 // reference only have 0): TransformIndexToPhysicalPoint sees index + region_index
+  double direction[9];          // row-major direction cosines; all zero or the identity: a non-oriented image
 };
 
 struct orc_mesh {
@@ -84,6 +93,8 @@ struct Geometry {
   double spacing[3];
   double origin[3];
   int64_t i0[3];  // image index of buffer voxel (0, 0, 0)
+  bool oriented;  // a non-identity direction matrix
+  double dir[9], m[9], minv[9];  // direction D, M = D*diag(spacing), M^-1 (row-major)
 };
 
 template <typename T>
@@ -116,13 +127,33 @@ inline void gradient_at(const Volume<T>& v, int64_t x, int64_t y, int64_t z, flo
     sum += c * hi;
     g[a] = sum;
   }
+  if (v.g.oriented) {  // GradientImageFilter::m_UseImageDirection: TransformLocalVectorToPhysicalVector
+    float r[3];
+    for (int i = 0; i < 3; ++i) {
+      double sum = 0.0;
+      for (int j = 0; j < 3; ++j) sum += v.g.dir[3 * i + j] * (double)g[j];
+      r[i] = (float)sum;
+    }
+    g[0] = r[0]; g[1] = r[1]; g[2] = r[2];
+  }
 }
 
 // Continuous index of a physical point (fp64): (p - origin) * (1/spacing)
 // (ImageBase::TransformPhysicalPointToContinuousIndex with a diagonal
 //  physical-to-index matrix; identity direction only).
 inline void cont_index(const Geometry& g, const double p[3], double ci[3]) {
-  for (int a = 0; a < 3; ++a) ci[a] = (p[a] - g.origin[a]) * (1.0 / g.spacing[a]);
+  if (!g.oriented) {
+    for (int a = 0; a < 3; ++a) ci[a] = (p[a] - g.origin[a]) * (1.0 / g.spacing[a]);
+    return;
+  }
+  // cvector = point - origin; cvector = m_PhysicalPointToIndex * cvector  (itk::Matrix * Vector: row sums from 0)
+  double c[3];
+  for (int a = 0; a < 3; ++a) c[a] = p[a] - g.origin[a];
+  for (int i = 0; i < 3; ++i) {
+    double sum = 0.0;
+    for (int j = 0; j < 3; ++j) sum += g.minv[3 * i + j] * c[j];
+    ci[i] = sum;
+  }
 }
 
 struct InterpSetup {
@@ -254,7 +285,14 @@ inline void project_vertex(const Volume<T>& v, const orc_params& P, double step0
 inline void corner_position(const Geometry& g, int64_t cx, int64_t cy, int64_t cz, float out[3]) {
   const int64_t idx[3] = {cx, cy, cz};
   for (int a = 0; a < 3; ++a) {
-    float p = (float)(g.spacing[a] * (double)(idx[a] + g.i0[a]) + g.origin[a]);  // TransformIndexToPhysicalPoint -> Point<float>
+    float p;
+    if (!g.oriented) {
+      p = (float)(g.spacing[a] * (double)(idx[a] + g.i0[a]) + g.origin[a]);  // TransformIndexToPhysicalPoint -> Point<float>
+    } else {
+      // point[i] = m_Origin[i]; for j: point[i] += m_IndexToPhysicalPoint[i][j] * index[j];   (Point<float>)
+      p = (float)g.origin[a];
+      for (int j = 0; j < 3; ++j) p = (float)((double)p + g.m[3 * a + j] * (double)(idx[j] + g.i0[j]));
+    }
     p = (float)((double)p - g.spacing[a] / 2.0);                     // vertex[a] -= spacing[a]/2.0
     out[a] = p;
   }
@@ -485,11 +523,31 @@ void sample_typed(const void* data, const Geometry& g, const double* pts, uint64
   }
 }
 
-Geometry make_geometry(const uint64_t dims[3], const double spacing[3], const double origin[3], const int64_t* i0 = nullptr) {
+Geometry make_geometry(const uint64_t dims[3], const double spacing[3], const double origin[3], const int64_t* i0 = nullptr,
+                       const double* direction = nullptr) {
   Geometry g;
   for (int a = 0; a < 3; ++a) g.i0[a] = i0 ? i0[a] : 0;
   g.nx = (int64_t)dims[0]; g.ny = (int64_t)dims[1]; g.nz = (int64_t)dims[2];
   for (int a = 0; a < 3; ++a) { g.spacing[a] = spacing ? spacing[a] : 1.0; g.origin[a] = origin ? origin[a] : 0.0; }
+  static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+  bool zero = true, ident = true;
+  for (int k = 0; k < 9; ++k) {
+    const double d = direction ? direction[k] : 0.0;
+    zero = zero && d == 0.0;
+    ident = ident && d == I[k];
+  }
+  g.oriented = direction && !zero && !ident;
+  for (int k = 0; k < 9; ++k) {
+    g.dir[k] = g.oriented ? direction[k] : I[k];
+    g.m[k] = g.dir[k] * g.spacing[k % 3];   // D * diag(spacing)
+  }
+  // cofactor inverse of M
+  const double* m = g.m;
+  const double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+  const double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+  g.minv[0] = c00 / det; g.minv[1] = (m[2] * m[7] - m[1] * m[8]) / det; g.minv[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+  g.minv[3] = c01 / det; g.minv[4] = (m[0] * m[8] - m[2] * m[6]) / det; g.minv[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+  g.minv[6] = c02 / det; g.minv[7] = (m[1] * m[6] - m[0] * m[7]) / det; g.minv[8] = (m[0] * m[4] - m[1] * m[3]) / det;
   return g;
 }
 
@@ -512,7 +570,7 @@ extern "C" {
 
 orc_mesh* orc_cuberille(const void* data, int dtype, const uint64_t dims[3], const double spacing[3],
                         const double origin[3], const orc_params* P) {
-  const Geometry g = make_geometry(dims, spacing, origin, P->region_index);
+  const Geometry g = make_geometry(dims, spacing, origin, P->region_index, P->direction);
   orc_mesh* m = nullptr;
   ORC_DISPATCH(dtype, m = run_typed<T>(data, g, *P));
   return m;
@@ -543,7 +601,7 @@ int orc_classify(const void* data, int dtype, const uint64_t dims[3], double iso
 // ProjectVertexToIsoSurface on caller points, in place.
 int orc_project_points(const void* data, int dtype, const uint64_t dims[3], const double spacing[3],
                        const double origin[3], const orc_params* P, float* pts, uint64_t n) {
-  const Geometry g = make_geometry(dims, spacing, origin, P->region_index);
+  const Geometry g = make_geometry(dims, spacing, origin, P->region_index, P->direction);
   ORC_DISPATCH(dtype, project_typed<T>(data, g, *P, pts, n));
   return 0;
 }

@@ -434,3 +434,149 @@ def test_streamed_slabs_from_host_memory(n_slabs, n_handles, resident):
     assert_mesh_equal(mesh, ref, "streamed")
     for h in handles:
         h.close()
+
+
+# ---- oriented images: direction matrices (cuberille_c.h cub_set_volume `direction`) ------------------
+_C30, _S30 = float(np.cos(np.pi / 6)), float(np.sin(np.pi / 6))
+DIRECTIONS = {
+    "flip_x": (-1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0),
+    "flip_yz": (1.0, 0.0, 0.0, 0.0, -1.0, 0.0, 0.0, 0.0, -1.0),
+    "permute": (0.0, 1.0, 0.0, 0.0, 0.0, 1.0, 1.0, 0.0, 0.0),
+    "rot_z_30": (_C30, -_S30, 0.0, _S30, _C30, 0.0, 0.0, 0.0, 1.0),
+    "oblique": tuple(float(v) for v in np.linalg.qr(np.random.default_rng(5).normal(size=(3, 3)))[0].reshape(9)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(DIRECTIONS))
+@pytest.mark.parametrize("dtype", [np.uint8, np.float32])
+@pytest.mark.parametrize("tri,proj", [(False, False), (True, True)])
+def test_direction_matrices(name, dtype, tri, proj):
+    """positions through M = D*diag(spacing), continuous indices through M^-1, rotated gradients: bit-exact vs the oracle"""
+    O, P = oracle(), pkg()
+    vol, iso = smooth_volume((22, 27, 40), dtype, seed=31)
+    D, sp, og = DIRECTIONS[name], (0.5, 1.25, 2.0), (3.0, -2.0, 7.0)
+    kw = dict(triangles=tri, project=proj, thr=0.02, step=0.24, relax=0.95, max_steps=80)
+    ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, spacing=sp, origin=og, direction=D, **kw)
+    mesh = run_filter(P.Image(vol, sp, og, D), iso, **kw)
+    assert_mesh_equal(mesh, ref, f"direction {name}")
+    if proj:  # the orientation does change the result (the test would pass trivially otherwise)
+        plain = O.cuberille(vol, iso, mode=O.CLOSED_FORM, spacing=sp, origin=og, **kw)
+        assert not np.array_equal(plain.points, ref.points)
+
+
+def test_direction_with_slabs_and_projection():
+    """z-slabs of an oriented image: the projection halo follows the z row of M^-1"""
+    O, P = oracle(), pkg()
+    vol, iso = smooth_volume((40, 20, 24), np.float32, seed=33)
+    D, sp = DIRECTIONS["rot_z_30"], (1.0, 1.0, 1.0)
+    prm = P.capi.default_params()
+    prm.iso_value, prm.generate_triangles, prm.project_vertices = float(iso), 1, 1
+    prm.surface_distance_threshold, prm.step_length, prm.max_steps = 0.02, 0.24, 80
+    ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, triangles=True, project=True, thr=0.02, step=0.24, relax=0.95, max_steps=80,
+                      spacing=sp, direction=D)
+    halo = max(P.capi.projection_halo(prm, sp))
+    pts, cells, pb, cb = [], [], 0, 0
+    for s in P.slabs.plan_slabs(vol.shape[0], 3, halo):
+        h = P.capi.Handle(0)
+        h.set_volume(vol[s.local_z0:s.local_z1], sp, (0.0, 0.0, 0.0), D)
+        h.set_slab(vol.shape[0], s.local_z0, s.own_z0, s.own_z1)
+        a, b = h.count(prm)
+        h.set_id_base(pb, cb)
+        h.emit(4)
+        x, y, _ = h.fetch()
+        pts.append(x); cells.append(y)
+        pb += a; cb += 2 * b
+        h.close()
+    assert_mesh_equal(P.Mesh(np.concatenate(pts), np.concatenate(cells)), ref, "oriented slabs")
+
+
+def test_emit_twice_gives_the_same_mesh():
+    """a second cub_emit on the same count (new id base, other id width) starts from unprojected points again"""
+    O, P = oracle(), pkg()
+    img = read_fixture("neghip")
+    h = P.capi.Handle(0)
+    h.set_volume(img.data)
+    p = P.capi.default_params()
+    p.iso_value, p.surface_distance_threshold, p.step_length, p.max_steps = 55.0, 0.2, 0.24, 3   # most vertices stop at max_steps
+    ref = O.cuberille(img.data, 55, triangles=True, project=True, thr=0.2, step=0.24, relax=0.95, max_steps=3)
+    h.count(p)
+    h.emit(4)
+    a = h.fetch()
+    h.emit(4)
+    b = h.fetch()
+    h.set_id_base(1000, 0)
+    h.emit(8)
+    c = h.fetch()
+    assert_mesh_equal(P.Mesh(a[0], a[1]), ref, "first emit")
+    assert_mesh_equal(P.Mesh(b[0], b[1]), ref, "second emit")
+    assert np.array_equal(c[0].view(np.uint32), ref.points.view(np.uint32)) and np.array_equal(c[1], ref.cells + 1000)
+    h.close()
+
+
+def test_async_pipeline_matches_and_survives_a_larger_second_run():
+    """cub_count_async / cub_emit_async / cub_finish: buffers sized by a small first run, then a larger volume on the same
+    handle overflows them on the device; cub_finish must redo the emission and return the complete mesh"""
+    O, P = oracle(), pkg()
+    h = P.capi.Handle(0)
+    p = P.capi.default_params()
+    p.generate_triangles, p.project_vertices, p.surface_distance_threshold = 1, 1, 0.02
+    for shape, seed in [((10, 12, 33), 1), ((30, 40, 70), 2), ((30, 40, 70), 3), ((12, 9, 20), 4)]:
+        vol, iso = smooth_volume(shape, np.float32, seed=seed)
+        p.iso_value = float(iso)
+        h.set_volume(vol)
+        h.count_async(p)
+        h.emit_async(4)
+        n_pts, n_cells = h.finish()
+        ref = O.cuberille(vol, iso, triangles=True, project=True, thr=0.02)
+        assert (n_pts, n_cells) == (ref.points.shape[0], ref.cells.shape[0])
+        a, b, _ = h.fetch()
+        assert_mesh_equal(P.Mesh(a, b), ref, f"async {shape}")
+    h.close()
+
+
+def test_empty_interior_slice_is_reported():
+    """the reference merges vertices across an empty slice; the library does not, and says so"""
+    P = pkg()
+    vol = np.zeros((9, 5, 5), np.uint8)
+    vol[2, 2, 2] = vol[4, 2, 2] = 255   # slice 3 is empty between two occupied ones
+    h = P.capi.Handle(0)
+    h.set_volume(vol)
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = 200.0, 0, 0
+    assert h.run(p) == (16, 12)
+    assert "empty voxel slice" in h.last_warning()
+    vol[3, 0, 0] = 255
+    h.set_volume(vol)
+    h.run(p)
+    assert h.last_warning() == ""
+    h.close()
+
+
+def test_slab_without_projection_halo_is_refused():
+    P = pkg()
+    vol, iso = smooth_volume((40, 16, 16), np.float32, seed=1)
+    h = P.capi.Handle(0)
+    h.set_volume(vol[8:32])
+    h.set_slab(40, 8, 10, 30)   # 2-slice halo: fine without projection, too short with it
+    p = P.capi.default_params()
+    p.iso_value, p.project_vertices = float(iso), 0
+    h.count(p)
+    p.project_vertices = 1
+    with pytest.raises(P.capi.CuberilleError) as e:
+        h.count(p)
+    assert "halo" in str(e.value)
+    h.close()
+
+
+def test_generated_slab_without_set_slab_is_refused():
+    """a generated z-slab (z_offset > 0) used without cub_set_slab wrote before its lattice"""
+    P = pkg()
+    h = P.capi.Handle(0)
+    h.generate(P.capi.GEN_GYROID, (32, 32, 16), (32, 32, 64), 20, 16.0)
+    p = P.capi.default_params()
+    p.iso_value, p.generate_triangles, p.project_vertices = 0.0, 0, 0
+    with pytest.raises(P.capi.CuberilleError):
+        h.count(p)
+    h.set_slab(64, 20, 22, 35)
+    h.count(p)
+    h.close()

@@ -4,7 +4,7 @@ Testing/CuberilleTest01.cxx:193-204) plus self-consistency of the restatement.""
 import numpy as np
 import pytest
 
-from util import KAT, KAT_ARGS, gyroid, oracle, random_volume, read_fixture
+from util import KAT, KAT_ARGS, gyroid, oracle, random_volume, read_fixture, smooth_volume
 
 
 @pytest.mark.parametrize("row", KAT, ids=[r[0] for r in KAT])
@@ -154,4 +154,49 @@ def test_oracle_params_struct_layout():
     body = body[:body.index("};")]
     names = re.findall(r"^\s*(?:double|int32_t|uint32_t|int64_t)\s+(\w+)", body, re.M)
     assert names == [n for n, _ in O._Params._fields_]
-    assert C.sizeof(O._Params) == 8 + 4 * 4 + 3 * 8 + 2 * 4 + 3 * 8
+    assert C.sizeof(O._Params) == 8 + 4 * 4 + 3 * 8 + 2 * 4 + 3 * 8 + 9 * 8
+
+
+# ---- oriented images: the oracle's restatement of ITK's direction-matrix semantics ---------------
+
+def test_oracle_identity_direction_is_the_non_oriented_image():
+    O = oracle()
+    vol, iso = smooth_volume((12, 14, 16), np.uint8, seed=2)
+    kw = dict(triangles=True, project=True, thr=0.05, spacing=(0.5, 1.0, 2.0), origin=(1.0, -2.0, 3.0))
+    a = O.cuberille(vol, iso, **kw)
+    b = O.cuberille(vol, iso, direction=(1, 0, 0, 0, 1, 0, 0, 0, 1), **kw)
+    assert np.array_equal(a.points.view(np.uint32), b.points.view(np.uint32)) and np.array_equal(a.cells, b.cells)
+
+
+def test_oracle_flipped_axis_positions():
+    """TransformIndexToPhysicalPoint with D = diag(-1, 1, 1) into a float point, then the reference's axis-aligned
+    half-spacing shift (txx:266-270), restated in numpy"""
+    O = oracle()
+    vol, iso = smooth_volume((9, 10, 11), np.uint8, seed=4)
+    sp, og = (0.7, 1.3, 2.1), (0.1, -5.25, 3.0)
+    D = (-1.0, 0, 0, 0, 1.0, 0, 0, 0, 1.0)
+    plain = O.cuberille(vol, iso, triangles=False, project=False, mode=O.CLOSED_FORM)
+    m = O.cuberille(vol, iso, triangles=False, project=False, mode=O.CLOSED_FORM, spacing=sp, origin=og, direction=D)
+    assert np.array_equal(m.cells, plain.cells)
+    idx = np.rint(plain.points + 0.5).astype(np.int64)   # lattice corner indices
+    M = np.array(D, np.float64).reshape(3, 3) * np.array(sp)[None, :]
+    exp = np.empty_like(plain.points)
+    for a in range(3):
+        p = np.full(idx.shape[0], np.float32(og[a]), np.float32)
+        for j in range(3):
+            p = (p.astype(np.float64) + M[a, j] * idx[:, j].astype(np.float64)).astype(np.float32)
+        exp[:, a] = (p.astype(np.float64) - sp[a] / 2.0).astype(np.float32)
+    assert np.array_equal(m.points.view(np.uint32), exp.view(np.uint32))
+
+
+def test_oracle_axis_permutation_is_equivariant():
+    """isotropic spacing, origin 0: with a permutation matrix as direction every operation of the oriented path is the
+    non-oriented one up to added zeros, so the mesh is the permuted mesh, bit for bit - projection included"""
+    O = oracle()
+    vol, iso = smooth_volume((14, 15, 16), np.float32, seed=8)
+    D = np.array([[0, 1, 0], [0, 0, 1], [1, 0, 0]], np.float64)   # physical axis i = index axis perm[i]
+    kw = dict(triangles=True, project=True, thr=0.02, step=0.24, relax=0.95, max_steps=60, spacing=(2.0, 2.0, 2.0))
+    a = O.cuberille(vol, iso, **kw)
+    b = O.cuberille(vol, iso, direction=D.reshape(9), **kw)
+    assert np.array_equal(a.cells, b.cells)
+    assert np.array_equal(b.points.view(np.uint32), (a.points @ D.T.astype(np.float32)).view(np.uint32))

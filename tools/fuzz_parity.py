@@ -29,11 +29,22 @@ while time.time() - t0 < budget:
     cd, border, raster = bool(rng.integers(2)), bool(rng.integers(2)), rng.random() < 0.25
     idb = 8 if rng.random() < 0.3 else 4
     geo = dict(spacing=tuple(float(x) for x in rng.choice([0.5, 1.0, 1.25, 2.0], 3)), origin=tuple(float(x) for x in rng.integers(-5, 6, 3)))
+    if rng.random() < 0.25:  # an oriented image: axis flips / permutations (exact) or a random rotation
+        if rng.random() < 0.5:
+            Dm = np.zeros((3, 3)); perm = rng.permutation(3)
+            for i_ in range(3):
+                Dm[i_, perm[i_]] = rng.choice([-1.0, 1.0])
+        else:
+            Dm = np.linalg.qr(rng.normal(size=(3, 3)))[0]
+        geo["direction"] = tuple(float(x) for x in Dm.reshape(9))
+        raster = False  # (the raster-order check sorts by physical coordinates)
     ridx = tuple(int(x) for x in rng.integers(-4, 5, 3)) if rng.random() < 0.3 else (0, 0, 0)
     what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} {geo}"
     kw = dict(triangles=tri, project=proj, cell_data=cd, thr=0.02)
     ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, border_faces=border, region_index=ridx, **kw, **geo)
     img = P.Image(vol, geo["spacing"], geo["origin"]); img.region_index = ridx
+    if "direction" in geo:
+        img.direction = geo["direction"]
     try:
         if raster:
             mesh = run_filter(img, iso, border_faces=border, raster_order=True, **kw)
@@ -58,10 +69,11 @@ while time.time() - t0 < budget:
                 # a projected vertex travels up to step / (1 - relax) = 5 * max spacing, i.e. many slices when the z
                 # spacing is the small one: give the slabs the whole image as halo then
                 halo = nz if proj else 2
+                dirn = geo.get("direction")
                 for z0, z1 in zip(cuts[:-1], cuts[1:]):
                     lo, hi = max(0, z0 - halo), min(nz, z1 + halo)
                     h = P.capi.Handle(0)
-                    h.set_volume(vol[lo:hi], geo["spacing"], geo["origin"]); h.set_region_index(ridx); h.set_slab(nz, lo, z0, z1)
+                    h.set_volume(vol[lo:hi], geo["spacing"], geo["origin"], dirn); h.set_region_index(ridx); h.set_slab(nz, lo, z0, z1)
                     a, b = h.count(prm)
                     if rng.random() < 0.5:
                         h.emit_vertices()
@@ -72,7 +84,7 @@ while time.time() - t0 < budget:
                 m2 = P.Mesh(np.concatenate(pts), np.concatenate(cells), np.concatenate(cds) if cd else None)
                 assert_mesh_equal(m2, ref, what + f" slabs {cuts}")
             # the same through slabs.run_streamed (host volume in, host mesh out, several handles / streams)
-            if nz >= 4 and not cd and rng.random() < 0.2:
+            if nz >= 4 and not cd and "direction" not in geo and rng.random() < 0.2:
                 import torch
                 n_sl, n_h, resident = int(rng.integers(2, min(nz, 6) + 1)), int(rng.integers(2, 4)), bool(rng.integers(2))
                 vt = torch.from_numpy(vol).pin_memory()
