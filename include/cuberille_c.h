@@ -270,6 +270,12 @@ int cub_device_alloc(cub_handle h, uint64_t bytes, void **out);
 int cub_device_free(cub_handle h, void *p);
 int cub_device_copy(cub_handle h, void *dst, const void *src, uint64_t bytes, int dst_kind, int src_kind);
 
+/* Page-lock / unlock a caller's host buffer (cudaHostRegister / cudaHostUnregister):
+ * an itk::Image buffer is pageable, and host <-> device copies of pageable memory
+ * run at a fraction of the PCIe rate.                                          */
+int cub_host_register(cub_handle h, void *p, uint64_t bytes);
+int cub_host_unregister(cub_handle h, void *p);
+
 /* Diagnostics for parity tests of the individual kernels.
  * cub_debug_bitmask: the 1-bit/voxel inside mask of the local buffer after
  * cub_count; words_per_row receives the row stride in 32-bit words; `out` (host)

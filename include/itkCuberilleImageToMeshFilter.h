@@ -22,14 +22,19 @@
  *  - TInterpolator must be itk::LinearInterpolateImageFunction<TInputImage>
  *    (the device kernel implements ITK's trilinear interpolation; another
  *    interpolator type raises an exception instead of being silently ignored);
- *  - the image direction must be the identity (exception otherwise); a buffered
- *    region that does not start at index 0 is passed on (cub_set_region_index);
+ *  - an oriented image (non-identity direction) is handled with ITK's oriented-image
+ *    arithmetic (cuberille_c.h, cub_set_volume); a buffered region that does not
+ *    start at index 0 is passed on (cub_set_region_index);
+ *  - an empty voxel slice between occupied ones, where the reference's lookup-plane
+ *    rotation merges vertices of different planes (txx:155-161), is meshed by the
+ *    intended rule and reported through itkWarningMacro (cub_last_warning);
  *  - a zero image gradient stops a vertex instead of dividing by zero (txx:452),
  *    out-of-image interpolation reads are clamped instead of undefined.
  *=========================================================================*/
 #ifndef __itkCuberilleImageToMeshFilter_h
 #define __itkCuberilleImageToMeshFilter_h
 
+#include <chrono>
 #include <cstdint>
 #include <type_traits>
 #include <vector>
@@ -41,6 +46,9 @@
 #include "itkTriangleCell.h"
 #include "itkQuadrilateralCell.h"
 #include "itkLinearInterpolateImageFunction.h"
+#include "itkVectorLinearInterpolateImageFunction.h"
+#include "itkConstShapedNeighborhoodIterator.h"
+#include "itkGradientImageFilter.h"
 #include "itkNumericTraits.h"
 
 #include "cuberille_c.h"
@@ -90,8 +98,10 @@ public:
   typedef typename OutputMeshType::CellIdentifier         CellIdentifier;
   typedef CellInterface<OutputPixelType, CellTraits>      CellInterfaceType;
   typedef TriangleCell<CellInterfaceType>                 TriangleCellType;
+  typedef typename TriangleCellType::SelfAutoPointer      TriangleAutoPointer;
   typedef typename TriangleCellType::CellAutoPointer      TriangleCellAutoPointer;
   typedef QuadrilateralCell<CellInterfaceType>            QuadrilateralCellType;
+  typedef typename QuadrilateralCellType::SelfAutoPointer QuadrilateralAutoPointer;
   typedef typename QuadrilateralCellType::CellAutoPointer QuadrilateralCellAutoPointer;
 
   typedef TInputImage                               InputImageType;
@@ -106,6 +116,19 @@ public:
 
   typedef TInterpolator                      InterpolatorType;
   typedef typename InterpolatorType::Pointer InterpolatorPointer;
+  typedef typename InterpolatorType::OutputType InterpolatorOutputType;
+
+  /** Other convenient typedefs of the reference (h:163-175).  The library evaluates the iterator's boundary
+   * condition, the gradient filter and its interpolator on the device; the types are exported because user code
+   * may name them. */
+  typedef ConstShapedNeighborhoodIterator< InputImageType > InputImageIteratorType;
+  typedef GradientImageFilter< InputImageType >             GradientFilterType;
+  typedef typename GradientFilterType::Pointer              GradientFilterPointer;
+  typedef typename GradientFilterType::OutputImageType      GradientImageType;
+  typedef typename GradientImageType::Pointer               GradientImagePointer;
+  typedef typename GradientFilterType::OutputPixelType      GradientPixelType;
+  typedef itk::VectorLinearInterpolateImageFunction< GradientImageType > GradientInterpolatorType;
+  typedef typename GradientInterpolatorType::Pointer        GradientInterpolatorPointer;
 
   /** Get/set the iso-surface value (h:180-181): pixels >= this value are inside (txx:139-141). */
   itkGetMacro( IsoSurfaceValue, InputPixelType );
@@ -163,6 +186,17 @@ public:
   itkGetMacro( Device, int );
   itkSetMacro( Device, int );
 
+  /** Page-lock the input image buffer while GenerateData() runs (cudaHostRegister), default off.  Speeds up the
+   * host -> device copy of large images; registering costs time of its own. */
+  itkGetMacro( PinInputBuffer, bool );
+  itkSetMacro( PinInputBuffer, bool );
+  itkBooleanMacro( PinInputBuffer );
+
+  /** Where the time of the last GenerateData() went, in milliseconds (host clock): [0] host -> device copy of the
+   * image, [1] the kernels (cub_run), [2] device -> host copy of the mesh, [3] filling the itk::Mesh (one heap cell
+   * per face, as ITK requires, txx:310-329), [4] total. */
+  const double * GetLastTimings() const { return m_LastTimings; }
+
 protected:
   CuberilleImageToMeshFilter()
     {
@@ -180,6 +214,8 @@ protected:
     m_ProjectVertexMaximumNumberOfSteps = 50;
     m_Device = 0;
     m_Handle = 0;
+    m_PinInputBuffer = false;
+    for ( int i = 0; i < 5; i++ ) { m_LastTimings[i] = 0.0; }
     }
 
   ~CuberilleImageToMeshFilter()
@@ -239,10 +275,19 @@ protected:
         itkExceptionMacro( << "cub_create failed: no usable CUDA device " << m_Device << " (there is no CPU fallback)" );
         }
       }
+    typedef std::chrono::steady_clock Clock;
+    const Clock::time_point t0 = Clock::now();
+    // an itk::Image buffer is pageable memory: the copy to the device then runs at a fraction of the PCIe rate.
+    // Page-locking it for the duration of the run (cudaHostRegister) is worth it for large images only.
+    const uint64_t imageBytes = dims[0] * dims[1] * dims[2] * sizeof( InputPixelType );
+    const bool pinned = m_PinInputBuffer &&
+      cub_host_register( m_Handle, const_cast<InputPixelType *>( image->GetBufferPointer() ), imageBytes ) == CUB_OK;
     this->Check( cub_set_volume( m_Handle, image->GetBufferPointer(),
                                  cuberille_detail::PixelCode<InputPixelType>::value,
                                  dims, spacing, origin, direction, CUB_MEM_HOST ) );
     this->Check( cub_set_region_index( m_Handle, regionIndex ) );
+    this->Check( cub_synchronize( m_Handle ) );
+    const Clock::time_point t1 = Clock::now();
     cub_params params;
     cub_default_params( &params );
     params.iso_value = static_cast<double>( m_IsoSurfaceValue );
@@ -256,15 +301,23 @@ protected:
     params.step_relaxation = m_ProjectVertexStepLengthRelaxationFactor;
     params.max_steps = m_ProjectVertexMaximumNumberOfSteps;
 
+    // PointIdentifier is unsigned long (64 bits), but a mesh of one handle has fewer than 2^32 points (cub_count
+    // refuses more): the ids travel as 32-bit values - half the bytes over PCIe - and are widened when the cells
+    // are created below.
     uint64_t numberOfPoints = 0, numberOfCells = 0;
-    this->Check( cub_run( m_Handle, &params, 8, &numberOfPoints, &numberOfCells ) );  // PointIdentifier: unsigned long
+    this->Check( cub_run( m_Handle, &params, 4, &numberOfPoints, &numberOfCells ) );
+    this->Check( cub_synchronize( m_Handle ) );
+    const Clock::time_point t2 = Clock::now();
+    const char * warning = cub_last_warning( m_Handle );
+    if ( warning && warning[0] ) { itkWarningMacro( << warning ); }
 
     const unsigned int verticesPerCell = m_GenerateTriangleFaces ? 3 : 4;
     std::vector<float> points( 3 * numberOfPoints );
-    std::vector<uint64_t> cells( verticesPerCell * numberOfCells );
+    std::vector<uint32_t> cells( verticesPerCell * numberOfCells );
     std::vector<InputPixelType> cellData( m_SavePixelAsCellData ? numberOfCells : 0 );
     this->Check( cub_fetch( m_Handle, points.empty() ? 0 : &points[0], cells.empty() ? 0 : &cells[0],
                             cellData.empty() ? 0 : &cellData[0], CUB_MEM_HOST ) );
+    const Clock::time_point t3 = Clock::now();
 
     // mesh->GetPoints()->InsertElement( id, vertex )   (txx:275)
     mesh->GetPoints()->Reserve( numberOfPoints );
@@ -301,6 +354,16 @@ protected:
         mesh->SetCellData( static_cast<CellIdentifier>( id ), static_cast<OutputPixelType>( cellData[id] ) );
         }
       }
+    if ( pinned )
+      {
+      cub_host_unregister( m_Handle, const_cast<InputPixelType *>( image->GetBufferPointer() ) );
+      }
+    const Clock::time_point t4 = Clock::now();
+    m_LastTimings[0] = std::chrono::duration<double, std::milli>( t1 - t0 ).count();
+    m_LastTimings[1] = std::chrono::duration<double, std::milli>( t2 - t1 ).count();
+    m_LastTimings[2] = std::chrono::duration<double, std::milli>( t3 - t2 ).count();
+    m_LastTimings[3] = std::chrono::duration<double, std::milli>( t4 - t3 ).count();
+    m_LastTimings[4] = std::chrono::duration<double, std::milli>( t4 - t0 ).count();
     }
 
 private:
@@ -328,6 +391,8 @@ private:
   unsigned int        m_ProjectVertexMaximumNumberOfSteps;
   int                 m_Device;
   cub_handle          m_Handle;
+  bool                m_PinInputBuffer;
+  double              m_LastTimings[5];
 };
 
 } // end namespace itk

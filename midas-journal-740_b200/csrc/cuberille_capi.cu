@@ -683,7 +683,7 @@ int count_launch(cub_handle h, const cub_params* p) {
   {
     if (h->timing) cudaEventRecord(h->ev[6], h->stream);
     SegScanArgs sa{};
-    sa.cnt = h->cnt.p; sa.seg = h->seg.p; sa.cofs = h->cofs.p;
+    sa.cnt = h->cnt.p; sa.seg = h->seg.p; sa.cofs = nullptr;  // (k_assign / k_points_raster write the dense slot bases, coalesced)
     sa.row_begin = (unsigned)row_begin; sa.n_rows = (unsigned)n_rows;
     sa.EW = (unsigned)h->EW; sa.NS = (unsigned)h->NS;
     sa.ghost_row_end = (unsigned)((size_t)h->zs0 * h->EY);
@@ -753,11 +753,19 @@ int count_finish(cub_handle h) {
 // guard their writes and flag an overflow).
 const int kNeedSizes = -1000;
 
-int emit_vertex_stage(cub_handle h, bool exact) {
+// quads, triangles with the fixed split, or quads into a scratch buffer that K5 splits by the diagonal test.
+// Unprojected quads of a non-oriented image are axis-aligned rectangles: both diagonals are equal in fp64 whatever
+// the spacing, `>=` takes the first split (txx:298-302), so the face kernel writes the triangles directly.  Projected
+// points, and the rounded points of an oriented image, need the test.
+int emit_mode(cub_handle h) {
   const cub_params& P = h->params;
+  if (!P.generate_triangles) return kEmitQuads;
+  return (P.project_vertices || h->geom.oriented) ? kEmitScratchQuads : kEmitTrisFixed;
+}
+
+int emit_vertex_stage(cub_handle h, bool exact) {
   const Grid& g = h->g;
-  const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0;
-  const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
+  const int mode = emit_mode(h);
   const int nz = h->zs1 - h->owner_z_min;
   if (exact) {
     const size_t n_pts_all = (size_t)(h->ghost_v + h->n_points);
@@ -783,11 +791,12 @@ int emit_vertex_stage(cub_handle h, bool exact) {
     {
       // K3a: vertex id -> lattice corner, walking the ownership masks K2a stored (reference creation order)
       AssignArgs a{};
-      a.cnt = h->cnt.p; a.own = h->own.p; a.seg = h->seg.p;
-      a.Wx = g.Wx; a.Y = g.Y; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.z_begin = h->owner_z_min;
+      a.cnt = h->cnt.p; a.own = h->own.p; a.seg = h->seg.p; a.cofs = h->cofs.p;
+      a.Wx = g.Wx; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.z_begin = h->owner_z_min;
+      a.ghost_row_end = (unsigned)((size_t)h->zs0 * h->EY);
       a.vtx = h->vtx.p; a.vtx_cap = cap; a.flags = h->d_info + kInfoFlags;
       const int rows = kAssignThreads / 32;
-      const dim3 grid((g.Wx + 31) / 32, (g.Y + rows - 1) / rows, nz);
+      const dim3 grid((g.Wx + 31) / 32, (h->EY + rows - 1) / rows, nz + 1);
       k_assign<<<grid, kAssignThreads, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
@@ -801,7 +810,9 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
       h->launches++;
       VertexArgs a{};
-      a.vtx = h->vtx.p; a.info = h->d_info; a.cap = cap; a.write_ghost_points = ghost_points ? 1 : 0;
+      a.vtx = h->vtx.p; a.cap = cap; a.write_ghost_points = ghost_points ? 1 : 0;
+      a.info = exact ? nullptr : h->d_info;
+      a.n_host = (size_t)(h->ghost_v + h->n_points); a.first_point_host = (size_t)h->ghost_v;
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
       a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
@@ -814,12 +825,13 @@ int emit_vertex_stage(cub_handle h, bool exact) {
   } else {
     // raster order: vertex id = corner slot, points straight from the active masks
     RasterPointArgs a{};
-    a.act = h->act.p; a.seg = h->seg.p; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.Wc = (g.X + 32) / 32;
-    a.plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1; a.plane_hi = h->zs1;
+    a.act = h->act.p; a.cofs = h->cofs.p; a.seg = h->seg.p; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.Wc = (g.X + 32) / 32;
+    a.plane_lo = h->zs0; a.plane_hi = h->zs1;
+    a.point_plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1;
     a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
     a.geom = h->geom; a.points = h->points.p; a.points_cap = h->points.cap / 3;
     a.flags = h->d_info + kInfoFlags;
-    const dim3 grid((a.Wc + 31) / 32, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
+    const dim3 grid((unsigned)h->NS, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
     k_points_raster<<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
@@ -832,7 +844,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
   const cub_params& P = h->params;
   const Grid& g = h->g;
   const bool tri = P.generate_triangles != 0, proj = P.project_vertices != 0, cd = P.save_pixel_as_cell_data != 0;
-  const int mode = !tri ? kEmitQuads : (proj ? kEmitScratchQuads : kEmitTrisFixed);
+  const int mode = emit_mode(h);
   h->verts_per_cell = tri ? 3 : 4;
   h->id_bytes = id_bytes;
   const size_t quad_bytes = (size_t)(tri ? 6 : 4) * id_bytes;   // cell bytes per quad
@@ -872,6 +884,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       a.info = h->d_info;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
       a.quads_cap = quads_cap;
+      a.guard = exact ? 0 : 1;
       a.mode = mode;
       a.vol = cd ? h->d_vol : nullptr;
       a.vX = h->gv.X; a.vY = h->gv.Y; a.vpad = h->pad; a.vzpad = h->zpad_lo;
@@ -1187,6 +1200,23 @@ int cub_device_copy(cub_handle h, void* dst, const void* src, uint64_t bytes, in
                                                       : (src_kind == CUB_MEM_DEVICE ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost);
   CU_TRY(h, cudaMemcpyAsync(dst, src, (size_t)bytes, k, h->stream));
   CU_TRY(h, cudaStreamSynchronize(h->stream));
+  return CUB_OK;
+}
+
+// Page-lock / unlock a caller buffer (cudaHostRegister): host <-> device copies of pageable memory run at a
+// fraction of the PCIe rate.
+int cub_host_register(cub_handle h, void* p, uint64_t bytes) {
+  if (!h || !p) return CUB_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaHostRegister(p, (size_t)bytes, cudaHostRegisterDefault));
+  return CUB_OK;
+}
+
+int cub_host_unregister(cub_handle h, void* p) {
+  if (!h || !p) return CUB_ERR_INVALID;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaHostUnregister(p));
   return CUB_OK;
 }
 

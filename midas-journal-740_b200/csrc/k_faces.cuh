@@ -30,6 +30,7 @@ struct FaceArgs {
   const uint4* seg;            // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   const uint32_t* perm;        // slot -> scan-relative vertex id
   const unsigned long long* info;  // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
+  int guard;                   // the host queued the launch without knowing the counts: check every cell against quads_cap
   void* cells;                 // final cells (IdT) or scratch quads (uint32 scan-relative ids)
   size_t quads_cap;            // quads the cell buffer can hold
   int mode;                    // kEmit*
@@ -58,7 +59,7 @@ __device__ __forceinline__ void store_tri_pair(IdT* c, IdT a0, IdT a1, IdT a2, I
 template <typename IdT, int MODE>
 __device__ __forceinline__ void write_cell(const FaceArgs& a, unsigned long long id_delta, uint32_t fidx, uint32_t q0,
                                            uint32_t q1, uint32_t q2, uint32_t q3) {
-  if (fidx >= a.quads_cap) return;  // (only when the caller queued the emission before it knew the counts: flagged by the kernel)
+  if (a.guard && fidx >= a.quads_cap) return;  // (flagged by the kernel; cub_finish redoes the emission)
   if (MODE == kEmitScratchQuads) {
     reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4(q0, q1, q2, q3);
     return;
@@ -93,7 +94,7 @@ __device__ __forceinline__ unsigned long long load_pixel(const void* vol, size_t
 
 template <int MODE>
 __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx, unsigned long long pix) {
-  if (fidx >= a.quads_cap) return;
+  if (a.guard && fidx >= a.quads_cap) return;
   const bool two = (MODE != kEmitQuads);
   const size_t c = two ? 2 * (size_t)fidx : (size_t)fidx;
   switch (a.pix_bytes) {
@@ -135,6 +136,9 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   const uint32_t e00 = ((uint32_t)zl * (uint32_t)a.EY + (uint32_t)y) * (uint32_t)a.EW + (uint32_t)w;  // corner word (w, y, z)
   uint32_t A[4] = {0, 0, 0, 0}, C[4] = {0, 0, 0, 0};
   uint32_t fseg = 0;
+  // (requested with everything else: the id base of a multi-GPU run only exists on the device)
+  const unsigned long long id_delta = __ldg(a.info + kInfoIdDelta);
+  const uint32_t ghost_f = (uint32_t)__ldg(a.info + kInfoMarkF);
   {
     // all the words are requested together (no early-out on an empty word: that would make the neighbour
     // loads wait for the first one, and the kernel is bound by its chain of dependent loads)
@@ -189,8 +193,6 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   }
   const uint32_t total = __shfl_sync(0xffffffffu, s0, 31) & 0xffffu;
   if (total == 0) return;  // no surface voxel in the 1024 voxels of the segment
-  const unsigned long long id_delta = __ldg(a.info + kInfoIdDelta);
-  const uint32_t ghost_f = (uint32_t)__ldg(a.info + kInfoMarkF);
 
   if (U) {
     s0 -= m0;  // exclusive
@@ -252,7 +254,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     if (f3) { write_cell<IdT, MODE>(a, id_delta, fi, vid[2], vid[3], vid[7], vid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f4) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[3], vid[2], vid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
     if (f5) { write_cell<IdT, MODE>(a, id_delta, fi, vid[4], vid[5], vid[6], vid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    overflow |= fi > a.quads_cap;
+    overflow |= a.guard && fi > a.quads_cap;
   }
   if (overflow) atomicOr(const_cast<unsigned long long*>(a.info) + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
 }

@@ -13,9 +13,10 @@
 // "one warp = 32 consecutive entries of a lattice row", so all it needs is the prefix at the START of its
 // segment: the rest is a warp shuffle scan of counts it has in registers anyway.  This kernel therefore writes
 // one uint4 {vertices, faces, active corners, -} per 32-entry segment of a row (NS = ceil(EW/32) segments per
-// row), plus ONE dense array, the active-corner prefix cofs (the slot bases): it is gathered per VERTEX by
-// k_vertices, which has no warp-per-row structure to scan in, and rebuilding it in k_faces with two more warp
-// scans cost more issue slots than the four loads (measured in r2).  4 B in, 4.5 B out per entry.
+// row): 4 B in, 0.5 B out per entry.  ONE dense array remains, the active-corner prefix cofs (the slot bases): it
+// is gathered per VERTEX by k_vertices, which has no warp-per-row structure to scan in, and rebuilding it in
+// k_faces with two more warp scans cost more issue slots than the four loads (measured in r2).  k_assign writes
+// it (coalesced, its warp scan carries the counts along); this kernel can too (`cofs`), with strided stores.
 //
 // Structure: one large tile (whole lattice rows) per resident CTA, chained with decoupled look-back (flag +
 // value in one 64-bit descriptor per tile and quantity, tiles handed out by an atomic ticket so that a tile

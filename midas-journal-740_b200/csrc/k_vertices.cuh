@@ -7,6 +7,9 @@
 //   K3a k_assign   one warp per 32-word segment of a voxel row.  K2a (k_sweep.cuh) decided, per voxel word, which
 //                  voxel owns which of its 8 local corners (8 masks, stored where the word owns anything); the
 //                  first id of a word is the segment base of k_seg_scan plus a warp scan of the words' counts.
+//                  The same scan carries the active-corner counts along and the warp writes the dense slot bases
+//                  cofs of its lattice row, coalesced (k_seg_scan, whose lanes own one row each, could only write
+//                  them with strided 16-byte stores: 0.21 ms against 0.08 ms without them).
 //                  Lanes whose word owns a corner walk the masks - voxels in bit order, local corners 0..7 - and
 //                  record for vertex id (first id + rank) the corner it sits on: cx | cy << 16 | oz << 31.
 //   K3b k_vertices one thread per vertex id, perfectly balanced and coalesced: reads the 4-byte record, writes the
@@ -29,11 +32,13 @@
 namespace cbr {
 
 struct AssignArgs {
-  const uint32_t* cnt;    // entry lattice: owned corners in the low 10 bits
+  const uint32_t* cnt;    // entry lattice: owned corners | faces << 10 | active corners << 20
   const uint4* own;       // entry lattice x 2: ownership masks O[0..3], O[4..7]
   const uint4* seg;       // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
-  int Wx, Y, EY, EW, NS;
-  int z_begin;            // first local slice of the scan range (blockIdx.z = 0)
+  uint32_t* cofs;         // entry lattice, written here: exclusive prefix of the active-corner counts (slot bases)
+  int Wx, EY, EW, NS;
+  int z_begin;            // first local plane of the scan range (blockIdx.z = 0)
+  unsigned ghost_row_end; // active corners of lattice rows below this one are not counted (the slab underneath owns them)
   uint32_t* vtx;          // [n vertices] cx | cy << 16 | oz << 31
   size_t vtx_cap;
   unsigned long long* flags;
@@ -41,23 +46,45 @@ struct AssignArgs {
 
 constexpr int kAssignThreads = 128;  // (one row segment per warp)
 
+// grid: x = 32-word segments of a voxel row, y = groups of kAssignThreads / 32 lattice rows (one row per warp),
+// z = planes of the scan range (one more than its voxel slices: the top corner plane)
 __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
-  // grid: x = 32-word segments of a row, y = groups of kAssignThreads / 32 rows (one row per warp), z = slices of the scan range
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
-  if (y >= a.Y) return;  // (warp-uniform)
+  if (y >= a.EY) return;  // (warp-uniform)
   const uint32_t row = (uint32_t)z * (uint32_t)a.EY + (uint32_t)y;
   const uint32_t e = row * (uint32_t)a.EW + (uint32_t)w;
-  const uint32_t nv = w < a.Wx ? (__ldg(a.cnt + e) & 0x3ffu) : 0u;
-  // first id of the word: segment base + exclusive warp scan of the owned-corner counts
-  uint32_t incl = nv;
+  const bool counted = row >= a.ghost_row_end;
+  // (entries that are not voxel words - the column past the last voxel word, the row y = Y, the top plane - have
+  //  no owned corners: K2a wrote 0 there)
+  const uint32_t c = w < a.EW ? __ldg(a.cnt + e) : 0u;
+  const uint4 sb = __ldg(a.seg + row * (uint32_t)a.NS + blockIdx.x);
+  const uint32_t nv = c & 0x3ffu, na = counted ? c >> 20 : 0u;
+  // one warp scan, two 16-bit fields: owned corners (first id of the word) | active corners (slot base of the word)
+  uint32_t incl = nv | (na << 16);
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
+  const uint32_t excl = incl - (nv | (na << 16));
+  if (w < a.EW) a.cofs[e] = sb.z + (excl >> 16);
+  if (blockIdx.x == gridDim.x - 1 && (int)(gridDim.x * 32) < a.EW) {
+    // the corner words past the last 32-word voxel segment of the row (warp-uniform branch; at most a few words)
+    for (int s = gridDim.x; s < a.NS; ++s) {
+      const int w2 = s * 32 + lane;
+      const uint32_t na2 = (w2 < a.EW && counted) ? __ldg(a.cnt + row * (uint32_t)a.EW + (uint32_t)w2) >> 20 : 0u;
+      uint32_t in2 = na2;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
+        if (lane >= o) in2 += t;
+      }
+      if (w2 < a.EW) a.cofs[row * (uint32_t)a.EW + (uint32_t)w2] = __ldg(&a.seg[row * (uint32_t)a.NS + s].z) + in2 - na2;
+    }
+  }
   if (nv == 0) return;
-  uint32_t n = __ldg(&a.seg[row * (uint32_t)a.NS + blockIdx.x].x) + incl - nv;
+  uint32_t n = sb.x + (excl & 0xffffu);
   if ((size_t)n + nv > a.vtx_cap) { atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow); return; }
   const uint4 lo = __ldcs(a.own + 2 * (size_t)e), hi = __ldcs(a.own + 2 * (size_t)e + 1);
   const uint32_t O[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
@@ -86,7 +113,8 @@ struct VertexArgs {
   const uint32_t* vtx;      // [n] packed corner of vertex id (scan-relative id): cx | cy << 16 | oz << 31
   const uint32_t* slice_first;  // [nz + 1] first id created by slice z_first + k; [nz] = UINT_MAX   (k_slice_index)
   const uint32_t* block_slice;  // [blocks of this launch] k of the block's first id                  (k_slice_index)
-  const unsigned long long* info;  // kInfoTotV: ghost vertices + own vertices; kInfoGhostV
+  const unsigned long long* info;  // kInfoTotV: ghost vertices + own vertices; kInfoGhostV; null: n_host / first_point_host hold them
+  size_t n_host, first_point_host;
   int z_first;              // first local slice of the scan range
   size_t cap;               // vertices the record / point buffers can hold
   int write_ghost_points;   // also write the points of the vertices that belong to the slab underneath
@@ -133,14 +161,16 @@ constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a ch
 
 __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
   // the number of vertices comes from the device-side run info (the grid may be sized for the buffer's capacity)
-  const size_t n_all = (size_t)__ldg(a.info + kInfoTotV);
+  // (read from the device only when the host queued the launch without knowing them: the load sits in front of
+  //  every other load of these short-lived blocks)
+  const size_t n_all = a.info ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
   const size_t n = n_all < a.cap ? n_all : a.cap;
   const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
   if ((size_t)blockIdx.x * kVertexBlockIds >= n) {
     if (n_all > a.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
     return;
   }
-  const size_t first_point = a.write_ghost_points ? 0 : (size_t)__ldg(a.info + kInfoGhostV);
+  const size_t first_point = a.write_ghost_points ? 0 : (a.info ? (size_t)__ldg(a.info + kInfoGhostV) : a.first_point_host);
   uint32_t v[kVertexPerThread];
 #pragma unroll
   for (int j = 0; j < kVertexPerThread; ++j) {
@@ -192,9 +222,11 @@ __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
 // masks: one thread per corner word, ids cseg[segment] + warp prefix + rank are consecutive inside a word.
 struct RasterPointArgs {
   const uint32_t* act;
+  uint32_t* cofs;           // entry lattice, written here: the slot base of every corner word (what k_assign writes in reference order)
   const uint4* seg;
   int EY, EW, NS, Wc;
-  int plane_lo, plane_hi;   // local corner planes to emit (inclusive)
+  int plane_lo, plane_hi;   // local corner planes of the launch (inclusive)
+  int point_plane_lo;       // first plane whose points are written (the bottom plane of a slab belongs to the slab underneath)
   int coff[3];              // as in VertexArgs
   Geom geom;
   float* points;            // indexed by slot
@@ -208,7 +240,7 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
   const int w = blockIdx.x * 32 + lane, cy = blockIdx.y * 8 + (threadIdx.x >> 5), cz = a.plane_lo + blockIdx.z;
   if (cy >= a.EY) return;
   const size_t row = (size_t)cz * a.EY + cy;
-  uint32_t m = w < a.Wc ? __ldg(a.act + row * a.EW + w) : 0u;
+  uint32_t m = w < a.Wc ? __ldg(a.act + row * a.EW + w) : 0u;   // (words Wc <= w < EW: never active)
   uint32_t incl = (uint32_t)__popc(m);
   const uint32_t mine = incl;
 #pragma unroll
@@ -216,8 +248,10 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
     const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
-  if (!m) return;
-  size_t id = (size_t)__ldg(a.seg + row * a.NS + blockIdx.x).z + (incl - mine);
+  const uint32_t base = __ldg(&a.seg[row * a.NS + blockIdx.x].z) + (incl - mine);
+  if (w < a.EW) a.cofs[row * a.EW + w] = base;
+  if (!m || cz < a.point_plane_lo) return;
+  size_t id = (size_t)base;
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;

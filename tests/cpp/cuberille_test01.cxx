@@ -9,6 +9,7 @@
 #include <zlib.h>
 
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -190,8 +191,69 @@ int Test01( int argc, char * argv [] )
     }
 }
 
+// `CuberilleTest01 DropInBench <size> [triangles] [project] [pin]`: the drop-in itself on a size^3 uint8 volume (a
+// gyroid quantised to 0..255, border forced outside): where the time of Update() goes - host -> device copy of the
+// (pageable) itk::Image buffer, kernels, device -> host copy of the mesh, filling the itk::Mesh (one heap cell per
+// face, as ITK requires).  Prints one JSON line.
+int DropInBench( int argc, char * argv [] )
+{
+  const unsigned long S = argc > 1 ? std::strtoul( argv[1], 0, 10 ) : 512;
+  const bool triangles = argc > 2 ? std::atoi( argv[2] ) != 0 : false, project = argc > 3 ? std::atoi( argv[3] ) != 0 : false;
+  const bool pin = argc > 4 ? std::atoi( argv[4] ) != 0 : false;
+  try
+    {
+    ImageType::Pointer image = ImageType::New();
+    ImageType::SizeType size; size[0] = size[1] = size[2] = S;
+    ImageType::IndexType start; start.Fill( 0 );
+    ImageType::RegionType region; region.SetSize( size ); region.SetIndex( start );
+    image->SetRegions( region );
+    image->Allocate();
+    PixelType * buf = image->GetBufferPointer();
+    const double k = 2.0 * 3.14159265358979323846 / 64.0;
+    std::vector<float> sn( S ), cs( S );
+    for ( unsigned long i = 0; i < S; i++ ) { sn[i] = (float)std::sin( k * i ); cs[i] = (float)std::cos( k * i ); }
+    for ( unsigned long z = 0; z < S; z++ )
+      for ( unsigned long y = 0; y < S; y++ )
+        for ( unsigned long x = 0; x < S; x++ )
+          {
+          const bool border = x == 0 || y == 0 || z == 0 || x == S - 1 || y == S - 1 || z == S - 1;
+          const float g = sn[x] * cs[y] + sn[y] * cs[z] + sn[z] * cs[x];
+          buf[( z * S + y ) * S + x] = border ? 0 : static_cast<PixelType>( 127.5f + g * 42.0f );
+          }
+    CuberilleType::Pointer filter = CuberilleType::New();
+    filter->SetInput( image );
+    filter->SetIsoSurfaceValue( 128 );
+    filter->SetGenerateTriangleFaces( triangles );
+    filter->SetProjectVerticesToIsoSurface( project );
+    filter->SetProjectVertexSurfaceDistanceThreshold( 0.5 );
+    filter->SetPinInputBuffer( pin );
+    double best[5] = { 0, 0, 0, 0, 1e300 };
+    unsigned long np = 0, nc = 0;
+    for ( int it = 0; it < 3; it++ )
+      {
+      filter->Modified();
+      filter->Update();
+      const double * t = filter->GetLastTimings();
+      if ( t[4] < best[4] ) { for ( int i = 0; i < 5; i++ ) best[i] = t[i]; }
+      np = filter->GetOutput()->GetNumberOfPoints(); nc = filter->GetOutput()->GetNumberOfCells();
+      }
+    std::cout << "{\"size\": " << S << ", \"pixel\": \"uint8\", \"triangles\": " << triangles << ", \"project\": " << project
+              << ", \"pin_input\": " << pin << ", \"n_points\": " << np << ", \"n_cells\": " << nc
+              << ", \"ms\": {\"h2d\": " << best[0] << ", \"kernels\": " << best[1] << ", \"d2h\": " << best[2]
+              << ", \"itk_mesh_fill\": " << best[3] << ", \"update_total\": " << best[4] << "}"
+              << ", \"gvoxels_per_s_update\": " << (double)S * S * S / ( best[4] * 1e-3 ) / 1e9 << "}" << std::endl;
+    return EXIT_SUCCESS;
+    }
+  catch ( itk::ExceptionObject & err )
+    {
+    std::cerr << "ExceptionObject caught !" << std::endl << err << std::endl;
+    return EXIT_FAILURE;
+    }
+}
+
 int main( int argc, char * argv [] )
 {
+  if ( argc > 1 && std::string( argv[1] ) == "DropInBench" ) { return DropInBench( argc - 1, argv + 1 ); }
   // `CuberilleTest01 Test01 <args>` (itkTestMain style, Testing/CMakeLists.txt:10-25) or `CuberilleTest01 <args>`
   if ( argc > 1 && std::string( argv[1] ) == "Test01" ) { return Test01( argc - 1, argv + 1 ); }
   return Test01( argc, argv );

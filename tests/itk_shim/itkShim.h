@@ -102,6 +102,10 @@ private:
   T * m_P;
 };
 
+#define itkWarningMacro( x )                                     \
+  { std::ostringstream itkmsg; itkmsg << "WARNING: In " __FILE__ ", line " << __LINE__ << "\n" \
+      << this->GetNameOfClass() << " (" << this << "): " x << "\n\n"; std::cerr << itkmsg.str(); }
+
 #define itkNewMacro( x )                                         \
   static Pointer New() { Pointer p = new x; return p; }
 
@@ -363,6 +367,28 @@ public:
   typedef double OutputType;
   itkNewMacro( Self );
   itkTypeMacro( LinearInterpolateImageFunction, Object );
+};
+
+// ---- types the reference header only names in typedefs (h:163-175) ---------------------------------------------
+template <typename TImage> class ConstShapedNeighborhoodIterator {};
+template <typename T, unsigned int D> struct CovariantVector { T m_V[D]; };
+template <typename TInputImage, typename TOperatorValueType = float, typename TOutputValueType = float>
+class GradientImageFilter : public ProcessObject
+{
+public:
+  typedef GradientImageFilter Self;
+  typedef SmartPointer<Self> Pointer;
+  typedef CovariantVector<TOutputValueType, 3> OutputPixelType;
+  typedef Image<OutputPixelType, 3> OutputImageType;
+  itkTypeMacro( GradientImageFilter, ProcessObject );
+};
+template <typename TInputImage, typename TCoordRep = double>
+class VectorLinearInterpolateImageFunction : public Object
+{
+public:
+  typedef VectorLinearInterpolateImageFunction Self;
+  typedef SmartPointer<Self> Pointer;
+  itkTypeMacro( VectorLinearInterpolateImageFunction, Object );
 };
 
 } // namespace itk

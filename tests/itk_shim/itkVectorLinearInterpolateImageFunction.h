@@ -1,0 +1,2 @@
+// forwarding header of the minimal ITK stand-in (tests/itk_shim/itkShim.h)
+#include "itkShim.h"
