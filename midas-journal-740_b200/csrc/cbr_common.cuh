@@ -63,9 +63,11 @@ struct Geom {
 //                                       p = (float)origin;  for j: p = (float)((double)p + M[a][j]*index[j])
 //   then, on every PHYSICAL axis (the reference does not rotate the shift, txx:268-270):
 //                                       p = (float)((double)p - spacing/2)
+// (ORIENTED is a template parameter of the kernels: the non-oriented instantiation must not carry the other path)
+template <bool ORIENTED>
 __device__ __forceinline__ float corner_coord(const Geom& g, int a, int ix, int iy, int iz) {
   float p;
-  if (!g.oriented) {
+  if (!ORIENTED) {
     const int idx = a == 0 ? ix : (a == 1 ? iy : iz);
     p = (float)__dadd_rn(__dmul_rn(g.spacing[a], (double)idx), g.origin[a]);
   } else {

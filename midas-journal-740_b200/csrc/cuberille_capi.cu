@@ -329,7 +329,8 @@ int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool incl
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
   const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)h->num_sms * h->knobs.proj_ctas);
-  DISPATCH_PIXEL(h->dtype, (k_project<T><<<blocks, 128, 0, h->stream>>>(a)));
+  if (h->geom.oriented) { DISPATCH_PIXEL(h->dtype, (k_project<T, true><<<blocks, 128, 0, h->stream>>>(a))); }
+  else { DISPATCH_PIXEL(h->dtype, (k_project<T, false><<<blocks, 128, 0, h->stream>>>(a))); }
   h->launches++;
   CU_TRY(h, cudaGetLastError());
   return CUB_OK;
@@ -811,14 +812,18 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       h->launches++;
       VertexArgs a{};
       a.vtx = h->vtx.p; a.cap = cap; a.write_ghost_points = ghost_points ? 1 : 0;
-      a.info = exact ? nullptr : h->d_info;
+      a.info = h->d_info;
       a.n_host = (size_t)(h->ghost_v + h->n_points); a.first_point_host = (size_t)h->ghost_v;
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
       a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
       a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
       a.points = h->points.p; a.perm = h->perm.p; a.perm_cap = h->perm.cap; a.flags = h->d_info + kInfoFlags;
-      k_vertices<<<n_blocks, 256, 0, h->stream>>>(a);
+      if (!exact) {
+        if (h->geom.oriented) k_vertices<true, true><<<n_blocks, 256, 0, h->stream>>>(a);
+        else k_vertices<false, true><<<n_blocks, 256, 0, h->stream>>>(a);
+      } else if (h->geom.oriented) k_vertices<true, false><<<n_blocks, 256, 0, h->stream>>>(a);
+      else k_vertices<false, false><<<n_blocks, 256, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     }
@@ -832,7 +837,8 @@ int emit_vertex_stage(cub_handle h, bool exact) {
     a.geom = h->geom; a.points = h->points.p; a.points_cap = h->points.cap / 3;
     a.flags = h->d_info + kInfoFlags;
     const dim3 grid((unsigned)h->NS, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
-    k_points_raster<<<grid, 256, 0, h->stream>>>(a);
+    if (h->geom.oriented) k_points_raster<true><<<grid, 256, 0, h->stream>>>(a);
+    else k_points_raster<false><<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
   }
@@ -884,7 +890,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       a.info = h->d_info;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
       a.quads_cap = quads_cap;
-      a.guard = exact ? 0 : 1;
+      a.perm_cap = h->perm.cap;
       a.mode = mode;
       a.vol = cd ? h->d_vol : nullptr;
       a.vX = h->gv.X; a.vY = h->gv.Y; a.vpad = h->pad; a.vzpad = h->zpad_lo;
@@ -893,8 +899,11 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       const dim3 blocks((g.Wx + 31) / 32, (g.Y + kFaceThreads / 32 - 1) / (kFaceThreads / 32), h->zs1 - h->zs0);
 #define CUB_FACES(IdT, MODE)                                                                   \
       do {                                                                                       \
-        if (cd) k_faces<IdT, MODE, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);             \
-        else k_faces<IdT, MODE, false><<<blocks, kFaceThreads, 0, h->stream>>>(a);               \
+        if (!exact) {                                                                            \
+          if (cd) k_faces<IdT, MODE, true, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);     \
+          else k_faces<IdT, MODE, false, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);       \
+        } else if (cd) k_faces<IdT, MODE, true, false><<<blocks, kFaceThreads, 0, h->stream>>>(a); \
+        else k_faces<IdT, MODE, false, false><<<blocks, kFaceThreads, 0, h->stream>>>(a);        \
       } while (0)
       if (mode == kEmitScratchQuads) CUB_FACES(uint32_t, kEmitScratchQuads);
       else if (mode == kEmitQuads && id_bytes == 4) CUB_FACES(uint32_t, kEmitQuads);
@@ -918,9 +927,9 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
     const size_t want = exact ? (size_t)h->n_quads : quads_cap;
     const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((want + 255) / 256, (size_t)h->num_sms * 16));
     if (id_bytes == 4)
-      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, h->d_info, quads_cap);
+      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, h->d_info, quads_cap, h->points.cap / 3);
     else
-      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, h->d_info, quads_cap);
+      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, h->d_info, quads_cap, h->points.cap / 3);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();

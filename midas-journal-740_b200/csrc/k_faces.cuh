@@ -30,7 +30,7 @@ struct FaceArgs {
   const uint4* seg;            // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   const uint32_t* perm;        // slot -> scan-relative vertex id
   const unsigned long long* info;  // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
-  int guard;                   // the host queued the launch without knowing the counts: check every cell against quads_cap
+  size_t perm_cap;             // entries of perm (GUARD instantiations check their slots against it)
   void* cells;                 // final cells (IdT) or scratch quads (uint32 scan-relative ids)
   size_t quads_cap;            // quads the cell buffer can hold
   int mode;                    // kEmit*
@@ -56,15 +56,16 @@ __device__ __forceinline__ void store_tri_pair(IdT* c, IdT a0, IdT a1, IdT a2, I
   }
 }
 
-template <typename IdT, int MODE>
-__device__ __forceinline__ void write_cell(const FaceArgs& a, unsigned long long id_delta, uint32_t fidx, uint32_t q0,
-                                           uint32_t q1, uint32_t q2, uint32_t q3) {
-  if (a.guard && fidx >= a.quads_cap) return;  // (flagged by the kernel; cub_finish redoes the emission)
+// v0..v3: FINAL vertex ids (the id offset is added once per corner by the caller, not once per face)
+// GUARD: the host queued the launch without knowing the counts (cub_emit_async): every cell is checked against the
+// capacity of the buffers (the kernel flags an overflow and cub_finish redoes the emission)
+template <typename IdT, int MODE, bool GUARD>
+__device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, IdT v0, IdT v1, IdT v2, IdT v3) {
+  if (GUARD && fidx >= a.quads_cap) return;
   if (MODE == kEmitScratchQuads) {
-    reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4(q0, q1, q2, q3);
+    reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, (uint32_t)v3);
     return;
   }
-  const IdT v0 = (IdT)(q0 + id_delta), v1 = (IdT)(q1 + id_delta), v2 = (IdT)(q2 + id_delta), v3 = (IdT)(q3 + id_delta);
   IdT* c = reinterpret_cast<IdT*>(a.cells);
   if (MODE == kEmitQuads) {
     c += (size_t)fidx * 4;
@@ -92,9 +93,9 @@ __device__ __forceinline__ unsigned long long load_pixel(const void* vol, size_t
   }
 }
 
-template <int MODE>
+template <int MODE, bool GUARD>
 __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx, unsigned long long pix) {
-  if (a.guard && fidx >= a.quads_cap) return;
+  if (GUARD && fidx >= a.quads_cap) return;
   const bool two = (MODE != kEmitQuads);
   const size_t c = two ? 2 * (size_t)fidx : (size_t)fidx;
   switch (a.pix_bytes) {
@@ -118,7 +119,7 @@ struct FaceSmem {
 // One thread per 32-voxel word computes the face masks; the surface voxels of a warp's 32 words are then
 // compacted into a queue and handled one per lane, so a word with ten surface voxels does not stall the 31
 // lanes whose words have none.
-template <typename IdT, int MODE, bool CD>
+template <typename IdT, int MODE, bool CD, bool GUARD>
 __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   const Grid& g = a.g;
@@ -242,19 +243,23 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
                             f0 || f1 || f5, f1 || f2 || f5, f2 || f3 || f5, f0 || f3 || f5};
 #pragma unroll
       for (int l = 0; l < 8; ++l)
-        if (need[l]) vid[l] = __ldg(a.perm + vid[l]);
+        if (need[l] && (!GUARD || vid[l] < a.perm_cap)) vid[l] = __ldg(a.perm + vid[l]);
     }
     // the voxel behind the face (cell data): word src of this warp's row
     const unsigned long long voxel =
         CD ? load_pixel(a.vol, ((size_t)(zl - a.vzpad) * a.vY + (size_t)(y - a.vpad)) * a.vX +
                                            (size_t)((sgm * 32 + src) * 32 + b - a.vpad), a.pix_bytes) : 0ull;
-    if (f0) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[4], vid[7], vid[3]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f1) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[1], vid[5], vid[4]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f2) { write_cell<IdT, MODE>(a, id_delta, fi, vid[1], vid[2], vid[6], vid[5]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f3) { write_cell<IdT, MODE>(a, id_delta, fi, vid[2], vid[3], vid[7], vid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f4) { write_cell<IdT, MODE>(a, id_delta, fi, vid[0], vid[3], vid[2], vid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    if (f5) { write_cell<IdT, MODE>(a, id_delta, fi, vid[4], vid[5], vid[6], vid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
-    overflow |= a.guard && fi > a.quads_cap;
+    // final ids: scan-relative id + id offset (scratch quads keep the scan-relative ids: K5 adds the offset)
+    IdT fid[8];
+#pragma unroll
+    for (int l = 0; l < 8; ++l) fid[l] = MODE == kEmitScratchQuads ? (IdT)vid[l] : (IdT)(vid[l] + id_delta);
+    if (f0) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[4], fid[7], fid[3]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (f1) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[1], fid[5], fid[4]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (f2) { write_cell<IdT, MODE, GUARD>(a, fi, fid[1], fid[2], fid[6], fid[5]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (f3) { write_cell<IdT, MODE, GUARD>(a, fi, fid[2], fid[3], fid[7], fid[6]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (f4) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[3], fid[2], fid[1]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (f5) { write_cell<IdT, MODE, GUARD>(a, fi, fid[4], fid[5], fid[6], fid[7]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
+    if (GUARD) overflow |= fi > a.quads_cap;
   }
   if (overflow) atomicOr(const_cast<unsigned long long*>(a.info) + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
 }
@@ -265,7 +270,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
 template <typename IdT>
 __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ quads, const float* __restrict__ points,
                                                      IdT* __restrict__ tris, const unsigned long long* __restrict__ info,
-                                                     size_t quads_cap) {
+                                                     size_t quads_cap, size_t points_cap) {
   // the number of quads and the id offset come from the device-side run info (no host round trip needed)
   const size_t n_all = (size_t)__ldg(info + kInfoQuads);
   const size_t n_quads = n_all < quads_cap ? n_all : quads_cap;
@@ -273,6 +278,8 @@ __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ q
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {
     const uint4 q = quads[i];
     const uint32_t id[4] = {q.x, q.y, q.z, q.w};
+    // (only after an overflow of the buffers of a cub_emit_async run, whose emission is redone anyway)
+    if (id[0] >= points_cap || id[1] >= points_cap || id[2] >= points_cap || id[3] >= points_cap) continue;
     float p[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k)

@@ -103,7 +103,7 @@ __device__ __forceinline__ int clampi(long long v, int hi) { return v < 0 ? 0 : 
 // Persistent lanes: the number of moves varies from 0 to max_steps+2 between vertices, so a lane that finishes
 // its vertex immediately takes the next one from a global counter instead of idling until the slowest vertex of
 // its warp is done.  The arithmetic per vertex is unchanged (and so are the results, bit for bit).
-template <typename T>
+template <typename T, bool ORIENTED>
 __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   VolView<T> v{static_cast<const T*>(a.vol), a.g.X, a.g.Y, a.g.Zl, a.g.zg0, a.g.Zg};
   float gc[3];
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     double dist[3];
     {
       double ci[3];
-      if (!a.geom.oriented) {
+      if (!ORIENTED) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) ci[k] = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
       } else {
@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           { float s = 0.0f; s += (-gc[0]) * xm; s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
           { float s = 0.0f; s += (-gc[1]) * ym; s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
           { float s = 0.0f; s += (-gc[2]) * zm; s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
-          if (a.geom.oriented) rotate_gradient(a.geom, ngrad[counter]);
+          if (ORIENTED) rotate_gradient(a.geom, ngrad[counter]);
         }
       } else {
 #pragma unroll 1
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
           float gtmp[3];
           gradient_at(v, gc, cx, cy, cz, gtmp);
-          if (a.geom.oriented) rotate_gradient(a.geom, gtmp);
+          if (ORIENTED) rotate_gradient(a.geom, gtmp);
           const double nv = (double)v.at(cx, cy, cz);
           // (dynamic index into the register cache: written through a switch so that it stays in registers)
 #pragma unroll
@@ -245,13 +245,14 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     double gd[3] = {0.0, 0.0, 0.0};
     double value = 0.0, total = 0.0;
     bool open = true;
+    // overlap = ((1 * wx) * wy) * wz in the reference's order; 1 * wx is wx, and the four wx * wy products are shared
+    // by the two z layers (same values, same association: bit-identical, 12 multiplications instead of 24)
+    const double wx[2] = {1.0 - dist[0], dist[0]}, wy[2] = {1.0 - dist[1], dist[1]}, wz[2] = {1.0 - dist[2], dist[2]};
+    const double wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
 #pragma unroll
     for (int counter = 0; counter < 8; ++counter) {
       if (open) {
-        double overlap = 1.0;
-        overlap *= (counter & 1) ? dist[0] : 1.0 - dist[0];
-        overlap *= (counter & 2) ? dist[1] : 1.0 - dist[1];
-        overlap *= (counter & 4) ? dist[2] : 1.0 - dist[2];
+        const double overlap = wxy[counter & 3] * wz[counter >> 2];
         if (overlap != 0.0) {
           gd[0] += overlap * (double)ngrad[counter][0];
           gd[1] += overlap * (double)ngrad[counter][1];
@@ -270,14 +271,34 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
       const double c = (double)normal[k];
       sq += c * c;
     }
-    const double norm = sqrt(sq);
-    if (norm == 0.0) {
-      done = true;  // zero gradient: the vertex stays where it is (DESIGN.md §2)
+    if (sq == 0.0) {   // norm == 0 (the square root of a positive double is positive)
+      done = true;  // zero gradient: the vertex stays where it is (DESIGN.md section 2)
     } else {
-#pragma unroll
-      for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
-      done |= fabs(value - a.iso) < a.thr;  // txx:456
+      done |= fabs(value - a.iso) < a.thr;  // txx:456  (the normalised normal is only used by the move below)
       if (!done) {
+        // normal[k] = (float)((double)normal[k] / sqrt(sq)), txx:452: an IEEE square root and three IEEE divisions
+        // (~120 instructions).  Fast path: q = normal[k] * rsqrt(sq) is within a few ulp (double) of the exact
+        // quotient, so it rounds to the same float unless it lies within 64 ulp of a float rounding boundary (the low
+        // 29 mantissa bits near 2^28) or the float result would be subnormal; only then (2.4e-7 of the cases) the
+        // exact expressions run.  The result is bit-identical to the oracle's either way.
+        const double r = rsqrt(sq);
+        float fast[3];
+        bool risky = !(sq >= 1e-280 && sq <= 1e280);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          const double q = (double)normal[k] * r;
+          fast[k] = (float)q;
+          const long long bits = __double_as_longlong(q);
+          const int low = (int)(bits & 0x1fffffffll) - 0x10000000;
+          risky |= (low > -64 && low < 64) || (normal[k] != 0.0f && fabs(q) < 2.4e-38);
+        }
+        if (risky) {
+          const double norm = sqrt(sq);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+        } else {
+          normal[0] = fast[0]; normal[1] = fast[1]; normal[2] = fast[2];
+        }
         const double sign = (value < a.iso) ? +1.0 : -1.0;  // txx:463
 #pragma unroll
         for (int k = 0; k < 3; ++k) vert[k] = (float)((double)vert[k] + ((double)normal[k] * sign) * step);  // txx:466

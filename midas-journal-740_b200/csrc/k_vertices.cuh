@@ -69,20 +69,10 @@ __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
   }
   const uint32_t excl = incl - (nv | (na << 16));
   if (w < a.EW) a.cofs[e] = sb.z + (excl >> 16);
-  if (blockIdx.x == gridDim.x - 1 && (int)(gridDim.x * 32) < a.EW) {
-    // the corner words past the last 32-word voxel segment of the row (warp-uniform branch; at most a few words)
-    for (int s = gridDim.x; s < a.NS; ++s) {
-      const int w2 = s * 32 + lane;
-      const uint32_t na2 = (w2 < a.EW && counted) ? __ldg(a.cnt + row * (uint32_t)a.EW + (uint32_t)w2) >> 20 : 0u;
-      uint32_t in2 = na2;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t t = __shfl_up_sync(0xffffffffu, in2, o);
-        if (lane >= o) in2 += t;
-      }
-      if (w2 < a.EW) a.cofs[row * (uint32_t)a.EW + (uint32_t)w2] = __ldg(&a.seg[row * (uint32_t)a.NS + s].z) + in2 - na2;
-    }
-  }
+  // the corner column past the last voxel word of the row, when it starts a segment of its own (X a multiple of 1024):
+  // it is the first word of that segment, its slot base is the segment base (the words after it are padding)
+  if (blockIdx.x == gridDim.x - 1 && lane == 0 && (int)(gridDim.x * 32) < a.EW)
+    a.cofs[row * (uint32_t)a.EW + gridDim.x * 32u] = __ldg(&a.seg[row * (uint32_t)a.NS + gridDim.x].z);
   if (nv == 0) return;
   uint32_t n = sb.x + (excl & 0xffffu);
   if ((size_t)n + nv > a.vtx_cap) { atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow); return; }
@@ -159,23 +149,37 @@ __global__ void __launch_bounds__(256) k_slice_index(const SliceIndexArgs a) {
 constexpr int kVertexPerThread = 4;                       // ids per thread: the loads of the 4 are in flight together
 constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a chain of 3 dependent loads otherwise)
 
+// GUARD: launched by cub_emit_async without the host knowing the counts (they are read from the device, every write
+// is checked against the capacity of its buffer)
+template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
   // the number of vertices comes from the device-side run info (the grid may be sized for the buffer's capacity)
   // (read from the device only when the host queued the launch without knowing them: the load sits in front of
   //  every other load of these short-lived blocks)
-  const size_t n_all = a.info ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
-  const size_t n = n_all < a.cap ? n_all : a.cap;
   const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
+  // GUARD: the count is read from the device; the records are requested first (any id below the capacity of the
+  // buffer is safe to read), so that the two loads overlap
+  uint32_t v[kVertexPerThread];
+  if (GUARD) {
+#pragma unroll
+    for (int j = 0; j < kVertexPerThread; ++j) {
+      const size_t id = id0 + (size_t)j * 256;
+      v[j] = id < a.cap ? __ldcs(a.vtx + id) : 0u;
+    }
+  }
+  const size_t n_all = GUARD ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
+  const size_t n = (!GUARD || n_all < a.cap) ? n_all : a.cap;
   if ((size_t)blockIdx.x * kVertexBlockIds >= n) {
-    if (n_all > a.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
+    if (GUARD && n_all > a.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
     return;
   }
-  const size_t first_point = a.write_ghost_points ? 0 : (a.info ? (size_t)__ldg(a.info + kInfoGhostV) : a.first_point_host);
-  uint32_t v[kVertexPerThread];
+  const size_t first_point = a.write_ghost_points ? 0 : (GUARD ? (size_t)__ldg(a.info + kInfoGhostV) : a.first_point_host);
+  if (!GUARD) {
 #pragma unroll
-  for (int j = 0; j < kVertexPerThread; ++j) {
-    const size_t id = id0 + (size_t)j * 256;
-    v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
+    for (int j = 0; j < kVertexPerThread; ++j) {
+      const size_t id = id0 + (size_t)j * 256;
+      v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
+    }
   }
   int lo = (int)__ldg(a.block_slice + blockIdx.x);
   int cz[kVertexPerThread];
@@ -205,14 +209,14 @@ __global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
     const int cx = (int)(v[j] & 0xffffu), cy = (int)((v[j] >> 16) & 0x7fffu);
     if (id >= first_point) {
       float* p = a.points + 3 * id;
-      p[0] = corner_coord(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
-      p[1] = corner_coord(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
-      p[2] = corner_coord(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
+      p[0] = corner_coord<ORIENTED>(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
+      p[1] = corner_coord<ORIENTED>(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
+      p[2] = corner_coord<ORIENTED>(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz[j] + a.coff[2]);
     }
     if (cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
       const uint32_t below = (1u << (cx & 31)) - 1u;
       const uint32_t slot = co[j] + __popc(ac[j] & below);
-      if (slot < a.perm_cap) a.perm[slot] = (uint32_t)id;
+      if (!GUARD || slot < a.perm_cap) a.perm[slot] = (uint32_t)id;
       else atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
     }
   }
@@ -234,6 +238,7 @@ struct RasterPointArgs {
   unsigned long long* flags;
 };
 
+template <bool ORIENTED>
 __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) {
   // grid: x = 32-word segments of a corner row, y = groups of 8 rows (one per warp), z = planes
   const int lane = threadIdx.x & 31;
@@ -258,9 +263,9 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
     if (id < a.points_cap) {
       float* p = a.points + 3 * id;
       const int cx = 32 * w + b;
-      p[0] = corner_coord(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-      p[1] = corner_coord(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-      p[2] = corner_coord(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
+      p[0] = corner_coord<ORIENTED>(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
+      p[1] = corner_coord<ORIENTED>(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
+      p[2] = corner_coord<ORIENTED>(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
     } else {
       atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
     }
