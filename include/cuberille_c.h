@@ -275,6 +275,10 @@ int cub_device_copy(cub_handle h, void *dst, const void *src, uint64_t bytes, in
  * run at a fraction of the PCIe rate.                                          */
 int cub_host_register(cub_handle h, void *p, uint64_t bytes);
 int cub_host_unregister(cub_handle h, void *p);
+/* Page-locked host memory (cudaHostAlloc / cudaFreeHost), e.g. staging buffers that
+ * cub_fetch fills at the full PCIe rate (the C++ adapter keeps a grow-only pair).  */
+int cub_host_alloc(cub_handle h, uint64_t bytes, void **out);
+int cub_host_free(cub_handle h, void *p);
 
 /* Diagnostics for parity tests of the individual kernels.
  * cub_debug_bitmask: the 1-bit/voxel inside mask of the local buffer after

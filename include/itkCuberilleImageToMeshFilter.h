@@ -216,11 +216,16 @@ protected:
     m_Handle = 0;
     m_PinInputBuffer = false;
     for ( int i = 0; i < 5; i++ ) { m_LastTimings[i] = 0.0; }
+    for ( int i = 0; i < 3; i++ ) { m_Staging[i] = 0; m_StagingBytes[i] = 0; }
     }
 
   ~CuberilleImageToMeshFilter()
     {
-    if ( m_Handle ) { cub_destroy( m_Handle ); }
+    if ( m_Handle )
+      {
+      for ( int i = 0; i < 3; i++ ) { if ( m_Staging[i] ) { cub_host_free( m_Handle, m_Staging[i] ); } }
+      cub_destroy( m_Handle );
+      }
     }
 
   void PrintSelf( std::ostream& os, Indent indent ) const
@@ -311,12 +316,17 @@ protected:
     const char * warning = cub_last_warning( m_Handle );
     if ( warning && warning[0] ) { itkWarningMacro( << warning ); }
 
+    // the mesh comes back through page-locked staging buffers that the filter keeps from run to run (grow-only):
+    // a fresh pageable std::vector costs more in page faults than the copy itself
     const unsigned int verticesPerCell = m_GenerateTriangleFaces ? 3 : 4;
-    std::vector<float> points( 3 * numberOfPoints );
-    std::vector<uint32_t> cells( verticesPerCell * numberOfCells );
-    std::vector<InputPixelType> cellData( m_SavePixelAsCellData ? numberOfCells : 0 );
-    this->Check( cub_fetch( m_Handle, points.empty() ? 0 : &points[0], cells.empty() ? 0 : &cells[0],
-                            cellData.empty() ? 0 : &cellData[0], CUB_MEM_HOST ) );
+    this->Stage( 0, 3 * numberOfPoints * sizeof( float ) );
+    this->Stage( 1, verticesPerCell * numberOfCells * sizeof( uint32_t ) );
+    this->Stage( 2, m_SavePixelAsCellData ? numberOfCells * sizeof( InputPixelType ) : 0 );
+    const float * points = static_cast<const float *>( m_Staging[0] );
+    const uint32_t * cells = static_cast<const uint32_t *>( m_Staging[1] );
+    const InputPixelType * cellData = static_cast<const InputPixelType *>( m_Staging[2] );
+    this->Check( cub_fetch( m_Handle, numberOfPoints ? static_cast<float *>( m_Staging[0] ) : 0, numberOfCells ? m_Staging[1] : 0,
+                            ( m_SavePixelAsCellData && numberOfCells ) ? m_Staging[2] : 0, CUB_MEM_HOST ) );
     const Clock::time_point t3 = Clock::now();
 
     // mesh->GetPoints()->InsertElement( id, vertex )   (txx:275)
@@ -370,6 +380,16 @@ private:
   CuberilleImageToMeshFilter(const Self&); //purposely not implemented
   void operator=(const Self&);             //purposely not implemented
 
+  /** page-locked staging buffer i of at least `bytes` bytes (grow-only) */
+  void Stage( int i, uint64_t bytes )
+    {
+    if ( bytes <= m_StagingBytes[i] ) { return; }
+    if ( m_Staging[i] ) { this->Check( cub_host_free( m_Handle, m_Staging[i] ) ); m_Staging[i] = 0; m_StagingBytes[i] = 0; }
+    const uint64_t want = bytes + bytes / 8;
+    this->Check( cub_host_alloc( m_Handle, want, &m_Staging[i] ) );
+    m_StagingBytes[i] = want;
+    }
+
   void Check( int status )
     {
     if ( status != CUB_OK )
@@ -393,6 +413,8 @@ private:
   cub_handle          m_Handle;
   bool                m_PinInputBuffer;
   double              m_LastTimings[5];
+  void *              m_Staging[3];
+  uint64_t            m_StagingBytes[3];
 };
 
 } // end namespace itk

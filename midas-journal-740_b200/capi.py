@@ -33,7 +33,7 @@ SYMBOLS = [
     "cub_projection_halo", "cub_count_async", "cub_device_counts", "cub_emit_async", "cub_finish", "cub_last_warning",
     "cub_comm_unique_id", "cub_comm_create", "cub_comm_destroy", "cub_comm_exchange_counts", "cub_comm_counts",
     "cub_comm_gather_mesh", "cub_device_alloc", "cub_device_free", "cub_device_copy",
-    "cub_host_register", "cub_host_unregister",
+    "cub_host_register", "cub_host_unregister", "cub_host_alloc", "cub_host_free",
 ]
 
 
@@ -144,6 +144,10 @@ def load() -> C.CDLL:
     L.cub_host_register.argtypes = [vp, vp, u64]
     L.cub_host_unregister.restype = i
     L.cub_host_unregister.argtypes = [vp, vp]
+    L.cub_host_alloc.restype = i
+    L.cub_host_alloc.argtypes = [vp, u64, C.POINTER(vp)]
+    L.cub_host_free.restype = i
+    L.cub_host_free.argtypes = [vp, vp]
     L.cub_comm_unique_id.restype = i
     L.cub_comm_unique_id.argtypes = [vp]
     L.cub_comm_create.restype = i

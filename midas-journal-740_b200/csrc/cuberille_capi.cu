@@ -1221,6 +1221,24 @@ int cub_host_register(cub_handle h, void* p, uint64_t bytes) {
   return CUB_OK;
 }
 
+// Page-locked host memory (cudaHostAlloc / cudaFreeHost): staging buffers for cub_fetch at the full PCIe rate.
+int cub_host_alloc(cub_handle h, uint64_t bytes, void** out) {
+  if (!h || !out) return CUB_ERR_INVALID;
+  *out = nullptr;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaHostAlloc(out, bytes ? (size_t)bytes : 1, cudaHostAllocDefault));
+  return CUB_OK;
+}
+
+int cub_host_free(cub_handle h, void* p) {
+  if (!h) return CUB_ERR_INVALID;
+  if (!p) return CUB_OK;
+  CU_TRY(h, cudaSetDevice(h->device));
+  CU_TRY(h, cudaStreamSynchronize(h->stream));
+  CU_TRY(h, cudaFreeHost(p));
+  return CUB_OK;
+}
+
 int cub_host_unregister(cub_handle h, void* p) {
   if (!h || !p) return CUB_ERR_INVALID;
   CU_TRY(h, cudaSetDevice(h->device));

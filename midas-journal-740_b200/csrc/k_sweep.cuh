@@ -52,6 +52,9 @@ struct SweepCfg {
   static constexpr int NT = NTX * NTY;               // live threads
   static constexpr int NTP = (NT + 31) / 32 * 32;    // launched threads
   static constexpr int NW = NTP / 32;
+  // resident CTAs the register allocation aims at: the (17, 7, 2) tile needs 6 x 128 threads per SM to hide its load
+  // chain (r1: 80 registers; the slice-occupancy flag of r2 pushed it to 88 = 5 CTAs, 376 -> 389 us)
+  static constexpr int MINB = (NTP == 128 && R_ == 2) ? 6 : 1;
   static constexpr int LO = 0;
   static constexpr int CR = NTY * R;                 // corner rows per CTA
   static constexpr int TXW = NTX - 1 - 2 * LO;       // voxel words (x) whose results the CTA produces
@@ -84,7 +87,7 @@ __device__ __forceinline__ void corner_owners(const uint32_t in[8], uint32_t vm,
 }
 
 template <typename C>
-__global__ void __launch_bounds__(C::NTP) k_sweep(const SweepArgs a) {
+__global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
   using S = SweepSmem<C>;
   constexpr int NTX = C::NTX, NTY = C::NTY, R = C::R, MODE = C::MODE, NT = C::NT, CR = C::CR;
   extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -152,7 +152,7 @@ constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a ch
 // GUARD: launched by cub_emit_async without the host knowing the counts (they are read from the device, every write
 // is checked against the capacity of its buffer)
 template <bool ORIENTED, bool GUARD>
-__global__ void __launch_bounds__(256) k_vertices(const VertexArgs a) {
+__global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const VertexArgs a) {
   // the number of vertices comes from the device-side run info (the grid may be sized for the buffer's capacity)
   // (read from the device only when the host queued the launch without knowing them: the load sits in front of
   //  every other load of these short-lived blocks)
