@@ -309,7 +309,17 @@ void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas
 
 // K4 on `pts` (explicit count n), or - from_info - on the handle's point buffer with the range taken from the
 // device-side run info (n = the capacity of the buffer)
-int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool include_ghost) {
+Caps make_caps(cub_handle h, unsigned long long quads_cap) {
+  Caps c;
+  c.raster = h->raster ? 1 : 0;
+  c.points = h->raster ? h->points.cap / 3 : std::min(h->points.cap / 3, h->vtx.cap);
+  c.perm = h->perm.cap;
+  c.quads = quads_cap;
+  return c;
+}
+
+int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool include_ghost, bool guard = false,
+                   unsigned long long quads_cap = ~0ull) {
   if (n == 0) return CUB_OK;
   ProjArgs a;
   a.vol = h->d_vol;
@@ -325,6 +335,8 @@ int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool incl
   a.n_points = n;
   a.info = from_info ? h->d_info : nullptr;
   a.include_ghost = include_ghost ? 1 : 0;
+  a.guard = guard ? 1 : 0;
+  a.caps = make_caps(h, quads_cap);
   a.work = h->d_info + kInfoWords;
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
@@ -795,10 +807,11 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       a.cnt = h->cnt.p; a.own = h->own.p; a.seg = h->seg.p; a.cofs = h->cofs.p;
       a.Wx = g.Wx; a.EY = h->EY; a.EW = h->EW; a.NS = h->NS; a.z_begin = h->owner_z_min;
       a.ghost_row_end = (unsigned)((size_t)h->zs0 * h->EY);
-      a.vtx = h->vtx.p; a.vtx_cap = cap; a.flags = h->d_info + kInfoFlags;
+      a.vtx = h->vtx.p; a.info = h->d_info; a.caps = make_caps(h, ~0ull);
       const int rows = kAssignThreads / 32;
       const dim3 grid((g.Wx + 31) / 32, (h->EY + rows - 1) / rows, nz + 1);
-      k_assign<<<grid, kAssignThreads, 0, h->stream>>>(a);
+      if (exact) k_assign<false><<<grid, kAssignThreads, 0, h->stream>>>(a);
+      else k_assign<true><<<grid, kAssignThreads, 0, h->stream>>>(a);
       h->launches++;
       CU_TRY(h, cudaGetLastError());
     }
@@ -811,14 +824,14 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
       h->launches++;
       VertexArgs a{};
-      a.vtx = h->vtx.p; a.cap = cap; a.write_ghost_points = ghost_points ? 1 : 0;
+      a.vtx = h->vtx.p; a.caps = make_caps(h, ~0ull); a.write_ghost_points = ghost_points ? 1 : 0;
       a.info = h->d_info;
       a.n_host = (size_t)(h->ghost_v + h->n_points); a.first_point_host = (size_t)h->ghost_v;
       a.slice_first = si.slice_first; a.block_slice = si.block_slice; a.z_first = h->owner_z_min;
       a.act = h->act.p; a.cofs = h->cofs.p; a.EY = h->EY; a.EW = h->EW;
       a.plane_lo = h->zs0; a.plane_hi = h->zs1; a.geom = h->geom;
       a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
-      a.points = h->points.p; a.perm = h->perm.p; a.perm_cap = h->perm.cap; a.flags = h->d_info + kInfoFlags;
+      a.points = h->points.p; a.perm = h->perm.p;
       if (!exact) {
         if (h->geom.oriented) k_vertices<true, true><<<n_blocks, 256, 0, h->stream>>>(a);
         else k_vertices<false, true><<<n_blocks, 256, 0, h->stream>>>(a);
@@ -834,11 +847,13 @@ int emit_vertex_stage(cub_handle h, bool exact) {
     a.plane_lo = h->zs0; a.plane_hi = h->zs1;
     a.point_plane_lo = (ghost_points || h->own_z0 == 0) ? h->zs0 : h->zs0 + 1;
     a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
-    a.geom = h->geom; a.points = h->points.p; a.points_cap = h->points.cap / 3;
-    a.flags = h->d_info + kInfoFlags;
+    a.geom = h->geom; a.points = h->points.p; a.info = h->d_info; a.caps = make_caps(h, ~0ull);
     const dim3 grid((unsigned)h->NS, (h->EY + 7) / 8, a.plane_hi - a.plane_lo + 1);
-    if (h->geom.oriented) k_points_raster<true><<<grid, 256, 0, h->stream>>>(a);
-    else k_points_raster<false><<<grid, 256, 0, h->stream>>>(a);
+    if (!exact) {
+      if (h->geom.oriented) k_points_raster<true, true><<<grid, 256, 0, h->stream>>>(a);
+      else k_points_raster<false, true><<<grid, 256, 0, h->stream>>>(a);
+    } else if (h->geom.oriented) k_points_raster<true, false><<<grid, 256, 0, h->stream>>>(a);
+    else k_points_raster<false, false><<<grid, 256, 0, h->stream>>>(a);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
   }
@@ -889,8 +904,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       a.act = h->act.p; a.cofs = h->cofs.p; a.seg = h->seg.p; a.perm = h->raster ? nullptr : h->perm.p;
       a.info = h->d_info;
       a.cells = (mode == kEmitScratchQuads) ? (void*)h->quads.p : (void*)h->cells.p;
-      a.quads_cap = quads_cap;
-      a.perm_cap = h->perm.cap;
+      a.caps = make_caps(h, quads_cap);
       a.mode = mode;
       a.vol = cd ? h->d_vol : nullptr;
       a.vX = h->gv.X; a.vY = h->gv.Y; a.vpad = h->pad; a.vzpad = h->zpad_lo;
@@ -918,7 +932,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
   }
   if (proj && (!exact || h->n_points > 0)) {
     Timer t(h, 3);
-    CUB_TRY(launch_project(h, h->points.p, h->points.cap / 3, true, ghost_points));
+    CUB_TRY(launch_project(h, h->points.p, h->points.cap / 3, true, ghost_points, !exact, quads_cap));
     h->projected = true;
     t.stop();
   }
@@ -927,9 +941,9 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
     const size_t want = exact ? (size_t)h->n_quads : quads_cap;
     const unsigned blocks = (unsigned)std::max<size_t>(1, std::min<size_t>((want + 255) / 256, (size_t)h->num_sms * 16));
     if (id_bytes == 4)
-      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, h->d_info, quads_cap, h->points.cap / 3);
+      k_split_quads<uint32_t><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (uint32_t*)h->cells.p, h->d_info, make_caps(h, quads_cap), exact ? 0 : 1);
     else
-      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, h->d_info, quads_cap, h->points.cap / 3);
+      k_split_quads<unsigned long long><<<blocks, 256, 0, h->stream>>>(h->quads.p, h->points.p, (unsigned long long*)h->cells.p, h->d_info, make_caps(h, quads_cap), exact ? 0 : 1);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     t.stop();

@@ -29,10 +29,9 @@ struct FaceArgs {
   const uint32_t* cofs;        // entry lattice, exclusive scan of the active-corner counts (slot bases)
   const uint4* seg;            // [lattice rows][NS] segment bases {vertices, faces, active corners, -}
   const uint32_t* perm;        // slot -> scan-relative vertex id
-  const unsigned long long* info;  // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
-  size_t perm_cap;             // entries of perm (GUARD instantiations check their slots against it)
+  unsigned long long* info;    // kInfoMarkF: scan offset of the first own face; kInfoIdDelta: scan-relative vertex id -> final id
+  Caps caps;                   // (GUARD instantiation only)
   void* cells;                 // final cells (IdT) or scratch quads (uint32 scan-relative ids)
-  size_t quads_cap;            // quads the cell buffer can hold
   int mode;                    // kEmit*
   const void* vol;             // for cell data (may be null)
   int vX, vY, vpad, vzpad;     // cell data: buffer row / slice size; lattice (x, y, z) is voxel (x - vpad, y - vpad, z - vzpad)
@@ -57,11 +56,8 @@ __device__ __forceinline__ void store_tri_pair(IdT* c, IdT a0, IdT a1, IdT a2, I
 }
 
 // v0..v3: FINAL vertex ids (the id offset is added once per corner by the caller, not once per face)
-// GUARD: the host queued the launch without knowing the counts (cub_emit_async): every cell is checked against the
-// capacity of the buffers (the kernel flags an overflow and cub_finish redoes the emission)
-template <typename IdT, int MODE, bool GUARD>
+template <typename IdT, int MODE>
 __device__ __forceinline__ void write_cell(const FaceArgs& a, uint32_t fidx, IdT v0, IdT v1, IdT v2, IdT v3) {
-  if (GUARD && fidx >= a.quads_cap) return;
   if (MODE == kEmitScratchQuads) {
     reinterpret_cast<uint4*>(a.cells)[fidx] = make_uint4((uint32_t)v0, (uint32_t)v1, (uint32_t)v2, (uint32_t)v3);
     return;
@@ -93,9 +89,8 @@ __device__ __forceinline__ unsigned long long load_pixel(const void* vol, size_t
   }
 }
 
-template <int MODE, bool GUARD>
+template <int MODE>
 __device__ __forceinline__ void write_celldata(const FaceArgs& a, uint32_t fidx, unsigned long long pix) {
-  if (GUARD && fidx >= a.quads_cap) return;
   const bool two = (MODE != kEmitQuads);
   const size_t c = two ? 2 * (size_t)fidx : (size_t)fidx;
   switch (a.pix_bytes) {
@@ -111,8 +106,10 @@ constexpr int kFaceThreads = 128;
 // per-word context a warp shares through shared memory: 4 x uint4
 //   [0] A[oz][oy]   active masks of the 4 corner words       [1] C[oz][oy]  their slot bases
 //   [2] F0..F3      [3] F4, F5, face base, -
+// (one array per uint4, the lane fastest: a lane stride of 16 bytes keeps the 128-bit stores of a warp free of bank
+//  conflicts; [lane][4] - a 64-byte stride - made them 4-way conflicts and cost the kernel 15 %)
 struct FaceSmem {
-  uint4 ctx[kFaceThreads / 32][32][4];
+  uint4 ctx[4][kFaceThreads / 32][32];
   uint16_t queue[kFaceThreads / 32][1024];         // (lane << 5) | bit of every surface voxel of the warp's words
 };
 
@@ -122,6 +119,9 @@ struct FaceSmem {
 template <typename IdT, int MODE, bool CD, bool GUARD>
 __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
+  // GUARD: the host queued the launch without knowing the counts (cub_emit_async): one check of the device-side
+  // counts against the capacity of the buffers, for the whole kernel
+  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // grid: x = 32-word segments of a row, y = groups of 4 rows (one row per warp), z = own slices.  128-thread CTAs:
@@ -197,11 +197,10 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
 
   if (U) {
     s0 -= m0;  // exclusive
-    uint4* cx = sm.ctx[warp][lane];
-    cx[0] = make_uint4(A[0], A[1], A[2], A[3]);
-    cx[1] = make_uint4(C[0], C[1], C[2], C[3]);
-    cx[2] = make_uint4(F[0], F[1], F[2], F[3]);
-    cx[3] = make_uint4(F[4], F[5], fseg + (s0 >> 16) - ghost_f, 0u);
+    sm.ctx[0][warp][lane] = make_uint4(A[0], A[1], A[2], A[3]);
+    sm.ctx[1][warp][lane] = make_uint4(C[0], C[1], C[2], C[3]);
+    sm.ctx[2][warp][lane] = make_uint4(F[0], F[1], F[2], F[3]);
+    sm.ctx[3][warp][lane] = make_uint4(F[4], F[5], fseg + (s0 >> 16) - ghost_f, 0u);
     uint32_t pos = s0 & 0xffffu;
     uint16_t* q = sm.queue[warp];
     const uint32_t tag = (uint32_t)lane << 5;
@@ -213,12 +212,10 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   }
   __syncwarp();
 
-  bool overflow = false;
   for (uint32_t s = lane; s < total; s += 32) {
     const uint32_t it = sm.queue[warp][s];
     const uint32_t src = it >> 5, b = it & 31u;
-    const uint4* cx = sm.ctx[warp][src];
-    const uint4 A4 = cx[0], C4 = cx[1], Fa = cx[2], Fb = cx[3];
+    const uint4 A4 = sm.ctx[0][warp][src], C4 = sm.ctx[1][warp][src], Fa = sm.ctx[2][warp][src], Fb = sm.ctx[3][warp][src];
     const uint32_t A[4] = {A4.x, A4.y, A4.z, A4.w}, C[4] = {C4.x, C4.y, C4.z, C4.w};
     const uint32_t Fm[6] = {Fa.x, Fa.y, Fa.z, Fa.w, Fb.x, Fb.y};
     const uint32_t bit = 1u << b, below = bit - 1u;
@@ -243,7 +240,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
                             f0 || f1 || f5, f1 || f2 || f5, f2 || f3 || f5, f0 || f3 || f5};
 #pragma unroll
       for (int l = 0; l < 8; ++l)
-        if (need[l] && (!GUARD || vid[l] < a.perm_cap)) vid[l] = __ldg(a.perm + vid[l]);
+        if (need[l]) vid[l] = __ldg(a.perm + vid[l]);
     }
     // the voxel behind the face (cell data): word src of this warp's row
     const unsigned long long voxel =
@@ -253,15 +250,13 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     IdT fid[8];
 #pragma unroll
     for (int l = 0; l < 8; ++l) fid[l] = MODE == kEmitScratchQuads ? (IdT)vid[l] : (IdT)(vid[l] + id_delta);
-    if (f0) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[4], fid[7], fid[3]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (f1) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[1], fid[5], fid[4]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (f2) { write_cell<IdT, MODE, GUARD>(a, fi, fid[1], fid[2], fid[6], fid[5]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (f3) { write_cell<IdT, MODE, GUARD>(a, fi, fid[2], fid[3], fid[7], fid[6]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (f4) { write_cell<IdT, MODE, GUARD>(a, fi, fid[0], fid[3], fid[2], fid[1]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (f5) { write_cell<IdT, MODE, GUARD>(a, fi, fid[4], fid[5], fid[6], fid[7]); if (CD) write_celldata<MODE, GUARD>(a, fi, voxel); ++fi; }
-    if (GUARD) overflow |= fi > a.quads_cap;
+    if (f0) { write_cell<IdT, MODE>(a, fi, fid[0], fid[4], fid[7], fid[3]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f1) { write_cell<IdT, MODE>(a, fi, fid[0], fid[1], fid[5], fid[4]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f2) { write_cell<IdT, MODE>(a, fi, fid[1], fid[2], fid[6], fid[5]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f3) { write_cell<IdT, MODE>(a, fi, fid[2], fid[3], fid[7], fid[6]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f4) { write_cell<IdT, MODE>(a, fi, fid[0], fid[3], fid[2], fid[1]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
+    if (f5) { write_cell<IdT, MODE>(a, fi, fid[4], fid[5], fid[6], fid[7]); if (CD) write_celldata<MODE>(a, fi, voxel); ++fi; }
   }
-  if (overflow) atomicOr(const_cast<unsigned long long*>(a.info) + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
 }
 
 // K5: triangle split of projected quads (AddQuadFace txx:286-321): reads the four PROJECTED points
@@ -269,17 +264,15 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
 // `>=` tie -> first split.
 template <typename IdT>
 __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ quads, const float* __restrict__ points,
-                                                     IdT* __restrict__ tris, const unsigned long long* __restrict__ info,
-                                                     size_t quads_cap, size_t points_cap) {
+                                                     IdT* __restrict__ tris, unsigned long long* __restrict__ info,
+                                                     Caps caps, int guard) {
   // the number of quads and the id offset come from the device-side run info (no host round trip needed)
-  const size_t n_all = (size_t)__ldg(info + kInfoQuads);
-  const size_t n_quads = n_all < quads_cap ? n_all : quads_cap;
+  if (guard && !emission_fits(info, caps)) { flag_overflow(info); return; }
+  const size_t n_quads = (size_t)__ldg(info + kInfoQuads);
   const unsigned long long id_delta = __ldg(info + kInfoIdDelta);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {
     const uint4 q = quads[i];
     const uint32_t id[4] = {q.x, q.y, q.z, q.w};
-    // (only after an overflow of the buffers of a cub_emit_async run, whose emission is redone anyway)
-    if (id[0] >= points_cap || id[1] >= points_cap || id[2] >= points_cap || id[3] >= points_cap) continue;
     float p[4][3];
 #pragma unroll
     for (int k = 0; k < 4; ++k)

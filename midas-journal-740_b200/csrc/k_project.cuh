@@ -31,9 +31,11 @@ struct ProjArgs {
   double relax;  // m_ProjectVertexStepLengthRelaxationFactor
   unsigned max_steps;
   float* points;
-  size_t n_points;           // number of points, or (info != null) the capacity of the point buffer
-  const unsigned long long* info;  // when set: the points are [ghost ? 0 : info[kInfoGhostV], info[kInfoGhostV] + info[kInfoPoints])
+  size_t n_points;           // number of points (info == null)
+  unsigned long long* info;  // when set: the points are [ghost ? 0 : info[kInfoGhostV], info[kInfoGhostV] + info[kInfoPoints])
   int include_ghost;
+  int guard;                 // queued before the host knew the counts: check them against caps first
+  Caps caps;
   long long i0[3];           // image index of buffer voxel (0, 0, 0) (cub_set_region_index): continuous indices are image indices
   unsigned long long* work;  // device counter (zeroed before the launch): next vertex to hand out
 };
@@ -116,10 +118,10 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   size_t n_points = a.n_points;
   float* const points = a.points + (a.info && !a.include_ghost ? 3 * (size_t)__ldg(a.info + kInfoGhostV) : 0);
   if (a.info) {
+    if (a.guard && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
     const size_t ghost = (size_t)__ldg(a.info + kInfoGhostV);
-    size_t all = ghost + (size_t)__ldg(a.info + kInfoPoints);
-    if (all > a.n_points) all = a.n_points;
-    n_points = a.include_ghost ? all : (all > ghost ? all - ghost : 0);
+    const size_t all = ghost + (size_t)__ldg(a.info + kInfoPoints);
+    n_points = a.include_ghost ? all : all - ghost;
   }
   size_t i = 0;
   bool have = false;
@@ -220,9 +222,13 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           const float xm = ax[oz][oy][ox], xp = ax[oz][oy][ox + 2];
           const float ym = oy == 0 ? ay[oz][0][ox] : ax[oz][0][ox + 1], yp = oy == 0 ? ax[oz][1][ox + 1] : ay[oz][1][ox];
           const float zm = oz == 0 ? az[0][oy][ox] : ax[0][oy][ox + 1], zp = oz == 0 ? ax[1][oy][ox + 1] : az[1][oy][ox];
-          { float s = 0.0f; s += (-gc[0]) * xm; s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
-          { float s = 0.0f; s += (-gc[1]) * ym; s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
-          { float s = 0.0f; s += (-gc[2]) * zm; s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
+          // sum = 0; sum += (-c) * I[-1]; sum += 0 * I[0]; sum += c * I[+1].  The middle term only matters for a
+          // non-finite centre pixel (0 * inf = NaN): for a finite one it adds +-0 to a sum that is never -0 (the
+          // first addition to +0 cleared the sign), i.e. nothing.
+          const bool odd = is_fp<T>::value && !(fabsf(mid) <= 3.402823466e38f);
+          { float s = 0.0f; s += (-gc[0]) * xm; if (odd) s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
+          { float s = 0.0f; s += (-gc[1]) * ym; if (odd) s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
+          { float s = 0.0f; s += (-gc[2]) * zm; if (odd) s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
           if (ORIENTED) rotate_gradient(a.geom, ngrad[counter]);
         }
       } else {
@@ -288,9 +294,10 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
         for (int k = 0; k < 3; ++k) {
           const double q = (double)normal[k] * r;
           fast[k] = (float)q;
-          const long long bits = __double_as_longlong(q);
-          const int low = (int)(bits & 0x1fffffffll) - 0x10000000;
-          risky |= (low > -64 && low < 64) || (normal[k] != 0.0f && fabs(q) < 2.4e-38);
+          // low 29 mantissa bits within 64 of the rounding boundary 2^28; |q| below the smallest normal float
+          // (biased exponent < 1023 - 126) unless it is an exact zero
+          const unsigned lo = (unsigned)__double2loint(q), hi = (unsigned)__double2hiint(q) & 0x7fffffffu;
+          risky |= ((lo & 0x1fffffffu) - (0x10000000u - 64u) < 128u) || (hi < 0x38100000u && (hi | lo) != 0u);
         }
         if (risky) {
           const double norm = sqrt(sq);

@@ -54,6 +54,22 @@ enum {
 };
 enum { kFlagBufferOverflow = 1, kFlagEmptyInteriorSlice = 2, kFlagIdOverflow = 4 };
 
+// Capacities of the result buffers, for launches queued before the host knows the counts (cub_emit_async): every
+// emission kernel compares them with the device-side counts ONCE, at its start, and the whole emission is skipped
+// (and flagged: cub_finish redoes it with larger buffers) if anything would not fit - no per-item checks.
+struct Caps {
+  unsigned long long points, perm, quads;
+  int raster;
+};
+__device__ __forceinline__ bool emission_fits(const unsigned long long* __restrict__ info, const Caps& c) {
+  const unsigned long long tv = __ldg(info + kInfoTotV), tc = __ldg(info + kInfoTotC);
+  const unsigned long long q = __ldg(info + kInfoTotF) - __ldg(info + kInfoMarkF);
+  return (c.raster ? tc : tv) <= c.points && (c.raster || tc <= c.perm) && q <= c.quads;
+}
+__device__ __forceinline__ void flag_overflow(unsigned long long* info) {
+  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicOr(info + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
+}
+
 struct SegScanArgs {
   const uint32_t* cnt;
   uint4* seg;                    // [rows of the lattice][NS] exclusive prefixes at the start of every segment

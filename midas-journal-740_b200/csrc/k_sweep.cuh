@@ -54,7 +54,7 @@ struct SweepCfg {
   static constexpr int NW = NTP / 32;
   // resident CTAs the register allocation aims at: the (17, 7, 2) tile needs 6 x 128 threads per SM to hide its load
   // chain (r1: 80 registers; the slice-occupancy flag of r2 pushed it to 88 = 5 CTAs, 376 -> 389 us)
-  static constexpr int MINB = (NTP == 128 && R_ == 2) ? 6 : 1;
+  static constexpr int MINB = 1;  // (forcing 6 CTAs = 80 registers was measured: 388 -> 404 us)
   static constexpr int LO = 0;
   static constexpr int CR = NTY * R;                 // corner rows per CTA
   static constexpr int TXW = NTX - 1 - 2 * LO;       // voxel words (x) whose results the CTA produces

@@ -40,15 +40,17 @@ struct AssignArgs {
   int z_begin;            // first local plane of the scan range (blockIdx.z = 0)
   unsigned ghost_row_end; // active corners of lattice rows below this one are not counted (the slab underneath owns them)
   uint32_t* vtx;          // [n vertices] cx | cy << 16 | oz << 31
-  size_t vtx_cap;
-  unsigned long long* flags;
+  unsigned long long* info;
+  Caps caps;              // (GUARD instantiation only)
 };
 
 constexpr int kAssignThreads = 128;  // (one row segment per warp)
 
 // grid: x = 32-word segments of a voxel row, y = groups of kAssignThreads / 32 lattice rows (one row per warp),
 // z = planes of the scan range (one more than its voxel slices: the top corner plane)
+template <bool GUARD>
 __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
+  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
   if (y >= a.EY) return;  // (warp-uniform)
@@ -60,6 +62,9 @@ __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
   const uint32_t c = w < a.EW ? __ldg(a.cnt + e) : 0u;
   const uint4 sb = __ldg(a.seg + row * (uint32_t)a.NS + blockIdx.x);
   const uint32_t nv = c & 0x3ffu, na = counted ? c >> 20 : 0u;
+  // the ownership masks are requested before the scan (the kernel is bound by this chain of dependent loads)
+  uint4 lo = make_uint4(0, 0, 0, 0), hi = lo;
+  if (nv) { lo = __ldcs(a.own + 2 * (size_t)e); hi = __ldcs(a.own + 2 * (size_t)e + 1); }
   // one warp scan, two 16-bit fields: owned corners (first id of the word) | active corners (slot base of the word)
   uint32_t incl = nv | (na << 16);
 #pragma unroll
@@ -75,8 +80,6 @@ __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
     a.cofs[row * (uint32_t)a.EW + gridDim.x * 32u] = __ldg(&a.seg[row * (uint32_t)a.NS + gridDim.x].z);
   if (nv == 0) return;
   uint32_t n = sb.x + (excl & 0xffffu);
-  if ((size_t)n + nv > a.vtx_cap) { atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow); return; }
-  const uint4 lo = __ldcs(a.own + 2 * (size_t)e), hi = __ldcs(a.own + 2 * (size_t)e + 1);
   const uint32_t O[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
   uint32_t U = O[0] | O[1] | O[2] | O[3] | O[4] | O[5] | O[6] | O[7];
   uint32_t* __restrict__ const out = a.vtx;
@@ -103,10 +106,10 @@ struct VertexArgs {
   const uint32_t* vtx;      // [n] packed corner of vertex id (scan-relative id): cx | cy << 16 | oz << 31
   const uint32_t* slice_first;  // [nz + 1] first id created by slice z_first + k; [nz] = UINT_MAX   (k_slice_index)
   const uint32_t* block_slice;  // [blocks of this launch] k of the block's first id                  (k_slice_index)
-  const unsigned long long* info;  // kInfoTotV: ghost vertices + own vertices; kInfoGhostV; null: n_host / first_point_host hold them
+  unsigned long long* info;  // GUARD: kInfoTotV = ghost vertices + own vertices, kInfoGhostV; else n_host / first_point_host hold them
   size_t n_host, first_point_host;
+  Caps caps;                // (GUARD instantiation only)
   int z_first;              // first local slice of the scan range
-  size_t cap;               // vertices the record / point buffers can hold
   int write_ghost_points;   // also write the points of the vertices that belong to the slab underneath
   const uint32_t* act;      // entry lattice [Zl+1][EY][EW]
   const uint32_t* cofs;
@@ -116,8 +119,6 @@ struct VertexArgs {
   Geom geom;
   float* points;            // indexed by scan-relative vertex id
   uint32_t* perm;           // [active corners of planes plane_lo..plane_hi] -> scan-relative vertex id
-  size_t perm_cap;
-  unsigned long long* flags;
 };
 
 // ids are handed out slice by slice, so the owner slice of an id follows from the per-slice first ids: this
@@ -153,33 +154,17 @@ constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a ch
 // is checked against the capacity of its buffer)
 template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const VertexArgs a) {
-  // the number of vertices comes from the device-side run info (the grid may be sized for the buffer's capacity)
-  // (read from the device only when the host queued the launch without knowing them: the load sits in front of
-  //  every other load of these short-lived blocks)
+  // GUARD: the number of vertices comes from the device-side run info (the grid is sized for the buffers' capacity)
+  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
   const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
-  // GUARD: the count is read from the device; the records are requested first (any id below the capacity of the
-  // buffer is safe to read), so that the two loads overlap
-  uint32_t v[kVertexPerThread];
-  if (GUARD) {
-#pragma unroll
-    for (int j = 0; j < kVertexPerThread; ++j) {
-      const size_t id = id0 + (size_t)j * 256;
-      v[j] = id < a.cap ? __ldcs(a.vtx + id) : 0u;
-    }
-  }
-  const size_t n_all = GUARD ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
-  const size_t n = (!GUARD || n_all < a.cap) ? n_all : a.cap;
-  if ((size_t)blockIdx.x * kVertexBlockIds >= n) {
-    if (GUARD && n_all > a.cap && blockIdx.x == 0 && threadIdx.x == 0) atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
-    return;
-  }
+  const size_t n = GUARD ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
+  if ((size_t)blockIdx.x * kVertexBlockIds >= n) return;
   const size_t first_point = a.write_ghost_points ? 0 : (GUARD ? (size_t)__ldg(a.info + kInfoGhostV) : a.first_point_host);
-  if (!GUARD) {
+  uint32_t v[kVertexPerThread];
 #pragma unroll
-    for (int j = 0; j < kVertexPerThread; ++j) {
-      const size_t id = id0 + (size_t)j * 256;
-      v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
-    }
+  for (int j = 0; j < kVertexPerThread; ++j) {
+    const size_t id = id0 + (size_t)j * 256;
+    v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
   }
   int lo = (int)__ldg(a.block_slice + blockIdx.x);
   int cz[kVertexPerThread];
@@ -215,9 +200,7 @@ __global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const Vertex
     }
     if (cz[j] >= a.plane_lo && cz[j] <= a.plane_hi) {
       const uint32_t below = (1u << (cx & 31)) - 1u;
-      const uint32_t slot = co[j] + __popc(ac[j] & below);
-      if (!GUARD || slot < a.perm_cap) a.perm[slot] = (uint32_t)id;
-      else atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
+      a.perm[co[j] + __popc(ac[j] & below)] = (uint32_t)id;
     }
   }
 }
@@ -234,12 +217,13 @@ struct RasterPointArgs {
   int coff[3];              // as in VertexArgs
   Geom geom;
   float* points;            // indexed by slot
-  size_t points_cap;
-  unsigned long long* flags;
+  unsigned long long* info;
+  Caps caps;                // (GUARD instantiation only)
 };
 
-template <bool ORIENTED>
+template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) {
+  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
   // grid: x = 32-word segments of a corner row, y = groups of 8 rows (one per warp), z = planes
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, cy = blockIdx.y * 8 + (threadIdx.x >> 5), cz = a.plane_lo + blockIdx.z;
@@ -260,15 +244,11 @@ __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) 
   while (m) {
     const int b = __ffs(m) - 1;
     m &= m - 1;
-    if (id < a.points_cap) {
-      float* p = a.points + 3 * id;
-      const int cx = 32 * w + b;
-      p[0] = corner_coord<ORIENTED>(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-      p[1] = corner_coord<ORIENTED>(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-      p[2] = corner_coord<ORIENTED>(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
-    } else {
-      atomicOr(a.flags, (unsigned long long)kFlagBufferOverflow);
-    }
+    float* p = a.points + 3 * id;
+    const int cx = 32 * w + b;
+    p[0] = corner_coord<ORIENTED>(a.geom, 0, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
+    p[1] = corner_coord<ORIENTED>(a.geom, 1, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
+    p[2] = corner_coord<ORIENTED>(a.geom, 2, cx + a.coff[0], cy + a.coff[1], cz + a.coff[2]);
     ++id;
   }
 }
