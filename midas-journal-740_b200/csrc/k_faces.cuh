@@ -120,8 +120,10 @@ template <typename IdT, int MODE, bool CD, bool GUARD>
 __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   __shared__ FaceSmem sm;
   // GUARD: the host queued the launch without knowing the counts (cub_emit_async): one check of the device-side
-  // counts against the capacity of the buffers, for the whole kernel
-  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+  // counts against the capacity of the buffers, for the whole kernel.  The counts are requested here and looked at
+  // after the scan, when every other load of the thread has come back too (a branch on them up here would put one
+  // more L2 round trip in front of each of these short-lived blocks).
+  const bool fits = !GUARD || emission_fits(a.info, a.caps);
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // grid: x = 32-word segments of a row, y = groups of 4 rows (one row per warp), z = own slices.  128-thread CTAs:
@@ -193,6 +195,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     if (lane >= o) s0 += t0;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, s0, 31) & 0xffffu;
+  if (GUARD && !fits) { flag_overflow(a.info); return; }
   if (total == 0) return;  // no surface voxel in the 1024 voxels of the segment
 
   if (U) {

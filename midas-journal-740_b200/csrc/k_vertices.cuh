@@ -50,7 +50,7 @@ constexpr int kAssignThreads = 128;  // (one row segment per warp)
 // z = planes of the scan range (one more than its voxel slices: the top corner plane)
 template <bool GUARD>
 __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
-  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+  const bool fits = !GUARD || emission_fits(a.info, a.caps);  // (looked at after the scan: see k_faces)
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
   if (y >= a.EY) return;  // (warp-uniform)
@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
     if (lane >= o) incl += t;
   }
   const uint32_t excl = incl - (nv | (na << 16));
+  if (GUARD && !fits) { flag_overflow(a.info); return; }
   if (w < a.EW) a.cofs[e] = sb.z + (excl >> 16);
   // the corner column past the last voxel word of the row, when it starts a segment of its own (X a multiple of 1024):
   // it is the first word of that segment, its slot base is the segment base (the words after it are padding)
@@ -155,16 +156,27 @@ constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a ch
 template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const VertexArgs a) {
   // GUARD: the number of vertices comes from the device-side run info (the grid is sized for the buffers' capacity)
-  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
   const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
+  uint32_t v[kVertexPerThread];
+  if (GUARD) {
+    // the records are requested before the counts are looked at (any id below the capacity of the buffer is safe
+    // to read), so that the two round trips overlap
+#pragma unroll
+    for (int j = 0; j < kVertexPerThread; ++j) {
+      const size_t id = id0 + (size_t)j * 256;
+      v[j] = id < a.caps.points ? __ldcs(a.vtx + id) : 0u;
+    }
+    if (!emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+  }
   const size_t n = GUARD ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
   if ((size_t)blockIdx.x * kVertexBlockIds >= n) return;
   const size_t first_point = a.write_ghost_points ? 0 : (GUARD ? (size_t)__ldg(a.info + kInfoGhostV) : a.first_point_host);
-  uint32_t v[kVertexPerThread];
+  if (!GUARD) {
 #pragma unroll
-  for (int j = 0; j < kVertexPerThread; ++j) {
-    const size_t id = id0 + (size_t)j * 256;
-    v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
+    for (int j = 0; j < kVertexPerThread; ++j) {
+      const size_t id = id0 + (size_t)j * 256;
+      v[j] = id < n ? __ldcs(a.vtx + id) : 0u;
+    }
   }
   int lo = (int)__ldg(a.block_slice + blockIdx.x);
   int cz[kVertexPerThread];
