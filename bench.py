@@ -509,6 +509,22 @@ def main():
         cpu = cpu_baseline_from_volume(get_slab, S, S, hi - lo, R.iso, args.cpu_seconds)
     R.close()
 
+    # ---- the drop-in itself: Update() of the C++ adapter (tests/cpp/cuberille_test01.cxx DropInBench) ---
+    if rank == 0 and N == 1 and not args.no_extras:
+        exe = os.path.join(ROOT, "tests", "cpp", "CuberilleTest01")
+        try:
+            if not os.path.exists(exe):
+                subprocess.check_call(["make", "-C", os.path.dirname(exe), "-s", "CuberilleTest01"])
+            runs = []
+            for a in (("512", "0", "0", "0"), ("512", "1", "1", "0")):
+                out = subprocess.run([exe, "DropInBench", *a], capture_output=True, text=True, timeout=300)
+                runs.append(json.loads(out.stdout.strip().splitlines()[-1]))
+            extras["cpp_adapter"] = {"runs": runs, "note": "itk::CuberilleImageToMeshFilter::Update() of include/itkCuberilleImageToMeshFilter.h on a "
+                                     "512^3 uint8 volume (pageable itk::Image buffer in, itk::Mesh out; tests/itk_shim stands in for ITK): host -> device "
+                                     "copy, kernels, device -> host copy into page-locked staging, itk::Mesh fill (one heap cell per face, txx:310-329)"}
+        except Exception as e:  # the C++ driver is optional for the bench line
+            extras["cpp_adapter"] = {"unavailable": str(e)[:200]}
+
     # ---- other workloads of BASELINE.json, where the driver can see them ------------------------------
     if not args.no_extras:
         if N == 1 and args.field == "gyroid" and S >= 512:

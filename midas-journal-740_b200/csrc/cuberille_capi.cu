@@ -80,6 +80,8 @@ cudaError_t dispatch_sweep(const SweepArgs& a, cudaStream_t st, int num_sms, int
   }
 }
 
+constexpr size_t kCtrlHead = kInfoWords + 4;  // info block, two work counters, the scan's ticket (+ pad)
+
 template <typename P>
 struct DevBuf {
   P* p = nullptr;
@@ -109,7 +111,11 @@ struct cub_handle_s {
   bool slab_set = false;
 
   // scratch
-  DevBuf<uint32_t> bits, cnt, act, cofs, perm, slice_any;
+  DevBuf<uint32_t> bits, cnt, act, cofs, perm;
+  // one control block, cleared with ONE memset per count: [info (kInfoWords + 2) | ticket | status (3 x tiles) | slice_any]
+  DevBuf<unsigned long long> ctrl;
+  uint32_t* d_slice_any = nullptr;
+  unsigned long long* d_status = nullptr;
   DevBuf<uint32_t> vtx;      // K3a -> K3b: the lattice corner of every vertex id
   DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
   DevBuf<uint4> own;         // K2a -> K3a: the 8 ownership masks per voxel word (2 x uint4 per entry)
@@ -118,8 +124,8 @@ struct cub_handle_s {
   uint64_t n_active = 0;     // active corners of the counted planes (size of the corner -> id map)
   bool raster = false;
   uint64_t bits_layout[3] = {0, 0, 0};
-  DevBuf<unsigned long long> status;  // 3 * n_tiles
   unsigned int* d_ticket = nullptr;
+  size_t ctrl_used = 0;
   unsigned long long* d_info = nullptr;  // kInfoWords (k_segscan.cuh) + 2 work counters
   unsigned long long* h_info = nullptr;  // pinned copy
 
@@ -432,9 +438,9 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
     h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
   }
-  bool ok = cudaMalloc(&h->d_ticket, sizeof(unsigned int)) == cudaSuccess &&
-            cudaMalloc(&h->d_info, (kInfoWords + 2) * sizeof(unsigned long long)) == cudaSuccess &&
+  bool ok = ensure(h, h->ctrl, kCtrlHead) == CUB_OK &&
             cudaMallocHost(&h->h_info, (kInfoWords + 2) * sizeof(unsigned long long)) == cudaSuccess;
+  if (ok) { h->d_info = h->ctrl.p; h->d_ticket = reinterpret_cast<unsigned int*>(h->ctrl.p + kInfoWords + 2); }
   for (int i = 0; ok && i < 10; ++i) ok = cudaEventCreate(&h->ev[i]) == cudaSuccess;
   if (!ok) { cub_destroy(h); return CUB_ERR_CUDA; }
   cub_default_params(&h->params);
@@ -448,8 +454,7 @@ int cub_destroy(cub_handle h) {
   cudaStreamSynchronize(h->stream);
   cudaFree(h->vol_owned.p);
   cudaFree(h->bits.p); cudaFree(h->cnt.p); cudaFree(h->act.p); cudaFree(h->perm.p); cudaFree(h->own.p); cudaFree(h->seg.p);
-  cudaFree(h->slice_any.p); cudaFree(h->status.p); cudaFree(h->cofs.p); cudaFree(h->vtx.p); cudaFree(h->vsl.p);
-  cudaFree(h->d_ticket); cudaFree(h->d_info);
+  cudaFree(h->ctrl.p); cudaFree(h->cofs.p); cudaFree(h->vtx.p); cudaFree(h->vsl.p);
   if (h->h_info) cudaFreeHost(h->h_info);
   cudaFree(h->points.p); cudaFree(h->cells.p); cudaFree(h->celldata.p); cudaFree(h->quads.p);
   for (int i = 0; i < 10; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -648,7 +653,6 @@ int count_launch(cub_handle h, const cub_params* p) {
   CUB_TRY(ensure(h, h->cnt, entries));
   CUB_TRY(ensure(h, h->act, entries + 4));
   CUB_TRY(ensure(h, h->seg, lattice_rows * h->NS));
-  CUB_TRY(ensure(h, h->slice_any, (size_t)g.Zl + 1));
   h->raster = p->vertex_order == CUB_ORDER_RASTER;
   CUB_TRY(ensure(h, h->cofs, entries + 4));
   if (!h->raster) CUB_TRY(ensure(h, h->own, 2 * entries));
@@ -670,11 +674,19 @@ int count_launch(cub_handle h, const cub_params* p) {
   size_t rows_per_tile = ((n_rows + max_tiles - 1) / max_tiles + kScanWarps - 1) / kScanWarps * kScanWarps;
   if (rows_per_tile < (size_t)kScanWarps) rows_per_tile = kScanWarps;
   const size_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
-  CUB_TRY(ensure(h, h->status, 3 * n_tiles));
+  {
+    const size_t need = kCtrlHead + 3 * n_tiles + ((size_t)g.Zl + 2 + 1) / 2;
+    CUB_TRY(ensure(h, h->ctrl, need));
+    h->d_info = h->ctrl.p;
+    h->d_ticket = reinterpret_cast<unsigned int*>(h->ctrl.p + kInfoWords + 2);
+    h->d_status = h->ctrl.p + kCtrlHead;
+    h->d_slice_any = reinterpret_cast<uint32_t*>(h->d_status + 3 * n_tiles);
+    h->ctrl_used = need;
+  }
   SweepArgs ca{};
   ca.bits = h->bits.p; ca.g = g; ca.Wc = Wc; ca.EY = h->EY; ca.EW = h->EW;
   ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = h->raster ? nullptr : h->own.p;
-  ca.slice_any = h->slice_any.p;
+  ca.slice_any = h->d_slice_any;
   {
     // K1 then K2a on the handle's stream.  (Running the HBM-bound K1 beside the issue-bound K2a, on two streams by
     // z-chunks or even without any dependency, was measured in r1 and took K1 + K2a: DESIGN.md section 8.)
@@ -684,10 +696,7 @@ int count_launch(cub_handle h, const cub_params* p) {
       CU_TRY(h, cudaGetLastError());
       t.stop();
     }
-    CU_TRY(h, cudaMemsetAsync(h->slice_any.p, 0, ((size_t)g.Zl + 1) * 4, h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->status.p, 0, 3 * n_tiles * sizeof(unsigned long long), h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->d_ticket, 0, sizeof(unsigned int), h->stream));
-    CU_TRY(h, cudaMemsetAsync(h->d_info, 0, (kInfoWords + 2) * sizeof(unsigned long long), h->stream));
+    CU_TRY(h, cudaMemsetAsync(h->ctrl.p, 0, h->ctrl_used * sizeof(unsigned long long), h->stream));
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
     ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
     CU_TRY(h, dispatch_sweep(ca, h->stream, h->num_sms, h->knobs.count_cfg));
@@ -705,11 +714,11 @@ int count_launch(cub_handle h, const cub_params* p) {
     // raster order: the corners of the bottom plane of a slab's range belong to the slab underneath
     sa.mark_row_c = (h->own_z0 > 0) ? (unsigned)((size_t)(h->zs0 + 1) * h->EY) : 0xffffffffu;
     sa.rows_per_tile = (unsigned)rows_per_tile; sa.n_tiles = (unsigned)n_tiles;
-    sa.status = h->status.p; sa.ticket = h->d_ticket; sa.info = h->d_info;
+    sa.status = h->d_status; sa.ticket = h->d_ticket; sa.info = h->d_info;
     k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
-    k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->slice_any.p, h->owner_z_min, h->zs1);
+    k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->d_slice_any, h->owner_z_min, h->zs1);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     if (h->timing) {

@@ -194,3 +194,55 @@ def test_headline_size_gyroid_1024_on_device():
         hh.close()
         del a, b
     assert (pbase, cbase) == (n_pts, n_quads)
+
+
+def test_blobs_1024_triangles_projection_slab_of_the_full_run_matches_the_oracle():
+    """BASELINE.json config 5 at one GPU's share (sphere blobs 1024^3 float32, triangles + projection).  The full run
+    stays on the device; a 16-slice z-slab of it with the projection halo is (a) run as a slab handle and compared
+    with the corresponding section of the full mesh, bytes for bytes, and (b) run through the oracle on the same
+    bytes (own range + halo as a stand-alone image: the halo keeps every read of the own range's vertices away from
+    the cut), ids shifted by the number of points the full run created before the slab."""
+    import torch
+    P, O = pkg(), oracle()
+    S, Z0, Z1 = 1024, 600, 616
+    dev = torch.device("cuda:0")
+    prm = P.capi.default_params()
+    prm.iso_value, prm.generate_triangles, prm.project_vertices, prm.surface_distance_threshold = 0.5, 1, 1, 0.005
+    below, above = P.capi.projection_halo(prm)
+    h = P.capi.Handle(0)
+    h.generate(P.capi.GEN_BLOBS, (S, S, S), p0=48.0, p1=1.0)
+    n_pts, n_cells = h.run(prm)
+    assert n_pts > 30_000_000 and n_cells == 2 * h.count(prm)[1]
+    h.emit(4)
+    pts = torch.empty((n_pts, 3), dtype=torch.float32, device=dev)
+    cells = torch.empty((n_cells, 3), dtype=torch.int32, device=dev)
+    h.fetch_into(pts.data_ptr(), cells.data_ptr(), 0, P.capi.MEM_DEVICE)
+    assert int(cells.max()) == n_pts - 1 and bool(torch.isfinite(pts).all())
+    h.close()
+    # how many points / cells exist when the raster loop enters slice Z0: a count-only handle over [0, Z0)
+    hb = P.capi.Handle(0)
+    hb.generate(P.capi.GEN_BLOBS, (S, S, Z0 + above), (S, S, S), 0, 48.0, 1.0)
+    hb.set_slab(S, 0, 0, Z0)
+    pbase, qbase = hb.count(prm)
+    hb.close()
+    # (a) the slab as a slab handle of the same image
+    lo, hi = Z0 - below, Z1 + above
+    hs = P.capi.Handle(0)
+    hs.generate(P.capi.GEN_BLOBS, (S, S, hi - lo), (S, S, S), lo, 48.0, 1.0)
+    hs.set_slab(S, lo, Z0, Z1)
+    np_, nq = hs.count(prm)
+    hs.set_id_base(pbase, 2 * qbase)
+    hs.emit(4)
+    sp, sc, _ = hs.fetch()
+    sub = hs.download_volume()
+    hs.close()
+    assert np.array_equal(sp.view(np.uint32), pts[pbase:pbase + np_].cpu().numpy().view(np.uint32)), "slab points differ from the full run"
+    assert np.array_equal(sc.view(np.int32), cells[2 * qbase:2 * qbase + 2 * nq].cpu().numpy()), "slab cells differ from the full run"
+    # (b) the oracle on the same bytes
+    ref = O.cuberille(sub, 0.5, triangles=True, project=True, thr=0.005)
+    pb, cb = ref.points_before_slice, ref.cells_before_slice
+    k0, k1 = Z0 - lo, Z1 - lo
+    assert int(pb[k1] - pb[k0]) == np_ and int(cb[k1] - cb[k0]) == 2 * nq
+    assert np.array_equal(ref.points[int(pb[k0]):int(pb[k1])].view(np.uint32), sp.view(np.uint32)), "projected points differ from the oracle"
+    shifted = ref.cells[int(cb[k0]):int(cb[k1])].astype(np.int64) - int(pb[k0]) + pbase
+    assert np.array_equal(shifted, sc.astype(np.int64)), "connectivity differs from the oracle"
