@@ -147,6 +147,7 @@ struct cub_handle_s {
   int zs0 = 0, zs1 = 0, owner_z_min = 0;
   bool vertices_done = false;   // the vertex stage of the current count has been queued (cub_emit_vertices)
   bool projected = false;       // the points of the current count have been projected in place
+  bool caps_checked = false;    // k_check_caps of the current emission has been queued
   uint64_t n_points = 0, n_quads = 0, n_cells = 0, ghost_v = 0, ghost_f = 0;
   uint64_t point_base = 0, cell_base = 0;
   uint64_t flags = 0;
@@ -732,6 +733,7 @@ int count_launch(cub_handle h, const cub_params* p) {
   h->count_queued = true;
   h->vertices_done = false;
   h->projected = false;
+  h->caps_checked = false;
   return CUB_OK;
 }
 
@@ -802,6 +804,13 @@ int emit_vertex_stage(cub_handle h, bool exact) {
   }
   h->vertices_done = true;
   h->projected = false;
+  if (!exact && !h->caps_checked) {
+    // the one comparison of the device-side counts with the capacity of the buffers (the quads are checked again,
+    // with the cell buffers of the emission, in emit_launch)
+    k_check_caps<<<1, 32, 0, h->stream>>>(h->d_info, make_caps(h, ~0ull));
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+  }
   // the points of the vertices the slab underneath owns are only needed by the projected triangle split
   const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
   if (!h->raster) {
@@ -895,6 +904,13 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
   if (cd) quads_cap = std::min(quads_cap, h->celldata.cap / cd_bytes);
 
   if (h->timing) cudaEventRecord(h->ev[4], h->stream);
+  if (!exact) {
+    // one comparison of the device-side counts with the capacity of the buffers, for every kernel of the emission
+    k_check_caps<<<1, 32, 0, h->stream>>>(h->d_info, make_caps(h, quads_cap));
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
+    h->caps_checked = true;
+  }
   const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
   // a second emit of the same count (another id width, new id bases) starts from unprojected points again
   if (proj && h->projected) h->vertices_done = false;

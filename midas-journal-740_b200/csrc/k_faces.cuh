@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
   // counts against the capacity of the buffers, for the whole kernel.  The counts are requested here and looked at
   // after the scan, when every other load of the thread has come back too (a branch on them up here would put one
   // more L2 round trip in front of each of these short-lived blocks).
-  const bool fits = !GUARD || emission_fits(a.info, a.caps);
+  const bool fits = !GUARD || emission_fits(a.info);
   const Grid& g = a.g;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // grid: x = 32-word segments of a row, y = groups of 4 rows (one row per warp), z = own slices.  128-thread CTAs:
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
     if (lane >= o) s0 += t0;
   }
   const uint32_t total = __shfl_sync(0xffffffffu, s0, 31) & 0xffffu;
-  if (GUARD && !fits) { flag_overflow(a.info); return; }
+  if (GUARD && !fits) return;
   if (total == 0) return;  // no surface voxel in the 1024 voxels of the segment
 
   if (U) {
@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(256) k_split_quads(const uint4* __restrict__ q
                                                      IdT* __restrict__ tris, unsigned long long* __restrict__ info,
                                                      Caps caps, int guard) {
   // the number of quads and the id offset come from the device-side run info (no host round trip needed)
-  if (guard && !emission_fits(info, caps)) { flag_overflow(info); return; }
+  if (guard && !emission_fits(info)) return;
   const size_t n_quads = (size_t)__ldg(info + kInfoQuads);
   const unsigned long long id_delta = __ldg(info + kInfoIdDelta);
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_quads; i += (size_t)gridDim.x * blockDim.x) {

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   size_t n_points = a.n_points;
   float* const points = a.points + (a.info && !a.include_ghost ? 3 * (size_t)__ldg(a.info + kInfoGhostV) : 0);
   if (a.info) {
-    if (a.guard && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+    if (a.guard && !emission_fits(a.info)) return;
     const size_t ghost = (size_t)__ldg(a.info + kInfoGhostV);
     const size_t all = ghost + (size_t)__ldg(a.info + kInfoPoints);
     n_points = a.include_ghost ? all : all - ghost;

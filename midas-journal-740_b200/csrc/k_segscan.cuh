@@ -50,6 +50,7 @@ enum {
   kInfoFlags = 12,                                  // bit 0: a result buffer was too small; bit 1: an interior slice of the range is empty
   kInfoWork = 13,                                   // work counter of the projection kernel
   kInfoSplitWork = 14,
+  kInfoFits = 15,                                   // written by k_check_caps: the queued emission fits its buffers
   kInfoWords = 16
 };
 enum { kFlagBufferOverflow = 1, kFlagEmptyInteriorSlice = 2, kFlagIdOverflow = 4 };
@@ -61,13 +62,16 @@ struct Caps {
   unsigned long long points, perm, quads;
   int raster;
 };
-__device__ __forceinline__ bool emission_fits(const unsigned long long* __restrict__ info, const Caps& c) {
-  const unsigned long long tv = __ldg(info + kInfoTotV), tc = __ldg(info + kInfoTotC);
-  const unsigned long long q = __ldg(info + kInfoTotF) - __ldg(info + kInfoMarkF);
-  return (c.raster ? tc : tv) <= c.points && (c.raster || tc <= c.perm) && q <= c.quads;
+// one thread, queued in front of an emission whose host does not know the counts: the verdict every GUARD kernel reads
+__global__ void k_check_caps(unsigned long long* info, Caps c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const unsigned long long tv = info[kInfoTotV], tc = info[kInfoTotC], q = info[kInfoTotF] - info[kInfoMarkF];
+  const bool fits = (c.raster ? tc : tv) <= c.points && (c.raster || tc <= c.perm) && q <= c.quads;
+  info[kInfoFits] = fits ? 1ull : 0ull;
+  if (!fits) info[kInfoFlags] |= (unsigned long long)kFlagBufferOverflow;
 }
-__device__ __forceinline__ void flag_overflow(unsigned long long* info) {
-  if (threadIdx.x == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) atomicOr(info + kInfoFlags, (unsigned long long)kFlagBufferOverflow);
+__device__ __forceinline__ bool emission_fits(const unsigned long long* __restrict__ info) {
+  return __ldg(info + kInfoFits) != 0ull;
 }
 
 struct SegScanArgs {

@@ -50,7 +50,7 @@ constexpr int kAssignThreads = 128;  // (one row segment per warp)
 // z = planes of the scan range (one more than its voxel slices: the top corner plane)
 template <bool GUARD>
 __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
-  const bool fits = !GUARD || emission_fits(a.info, a.caps);  // (looked at after the scan: see k_faces)
+  const bool fits = !GUARD || emission_fits(a.info);  // (looked at after the scan: see k_faces)
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
   if (y >= a.EY) return;  // (warp-uniform)
@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
     if (lane >= o) incl += t;
   }
   const uint32_t excl = incl - (nv | (na << 16));
-  if (GUARD && !fits) { flag_overflow(a.info); return; }
+  if (GUARD && !fits) return;
   if (w < a.EW) a.cofs[e] = sb.z + (excl >> 16);
   // the corner column past the last voxel word of the row, when it starts a segment of its own (X a multiple of 1024):
   // it is the first word of that segment, its slot base is the segment base (the words after it are padding)
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const Vertex
       const size_t id = id0 + (size_t)j * 256;
       v[j] = id < a.caps.points ? __ldcs(a.vtx + id) : 0u;
     }
-    if (!emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+    if (!emission_fits(a.info)) return;
   }
   const size_t n = GUARD ? (size_t)__ldg(a.info + kInfoTotV) : a.n_host;
   if ((size_t)blockIdx.x * kVertexBlockIds >= n) return;
@@ -235,7 +235,7 @@ struct RasterPointArgs {
 
 template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256) k_points_raster(const RasterPointArgs a) {
-  if (GUARD && !emission_fits(a.info, a.caps)) { flag_overflow(a.info); return; }
+  if (GUARD && !emission_fits(a.info)) return;
   // grid: x = 32-word segments of a corner row, y = groups of 8 rows (one per warp), z = planes
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, cy = blockIdx.y * 8 + (threadIdx.x >> 5), cz = a.plane_lo + blockIdx.z;

@@ -239,7 +239,8 @@ def test_blobs_1024_triangles_projection_slab_of_the_full_run_matches_the_oracle
     assert np.array_equal(sp.view(np.uint32), pts[pbase:pbase + np_].cpu().numpy().view(np.uint32)), "slab points differ from the full run"
     assert np.array_equal(sc.view(np.int32), cells[2 * qbase:2 * qbase + 2 * nq].cpu().numpy()), "slab cells differ from the full run"
     # (b) the oracle on the same bytes
-    ref = O.cuberille(sub, 0.5, triangles=True, project=True, thr=0.005)
+    # (the slab sits at image index (0, 0, lo): the same physical coordinates, so the same float roundings)
+    ref = O.cuberille(sub, 0.5, triangles=True, project=True, thr=0.005, region_index=(0, 0, lo))
     pb, cb = ref.points_before_slice, ref.cells_before_slice
     k0, k1 = Z0 - lo, Z1 - lo
     assert int(pb[k1] - pb[k0]) == np_ and int(cb[k1] - cb[k0]) == 2 * nq
