@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CUB_ABI_VERSION 2
+#define CUB_ABI_VERSION 3
 
 /* ---- status codes ------------------------------------------------------- */
 enum {
@@ -49,6 +49,9 @@ enum {
   CUB_MEM_HOST = 0,        /* pageable or pinned host memory                  */
   CUB_MEM_DEVICE = 1       /* device memory on the handle's device            */
 };
+
+/* ---- ProjectVertexToIsoSurface variants (h:22-23) ---------------------------- */
+enum { CUB_PROJECT_DEFAULT = 0, CUB_PROJECT_ADVANCED = 1, CUB_PROJECT_LINESEARCH = 2 };
 
 /* ---- vertex numbering ----------------------------------------------------- */
 enum { CUB_ORDER_REFERENCE = 0, CUB_ORDER_RASTER = 1 };
@@ -80,6 +83,11 @@ typedef struct cub_params {
                                  * the image counts as outside the surface, i.e. the mesh of the
                                  * image padded with one outside layer: always closed (the
                                  * "handle voxels on the edge of the image" TODO, txx:133)       */
+  int32_t  projection_method;   /* CUB_PROJECT_DEFAULT: the branch the reference compiles (txx:440-474).
+                                 * CUB_PROJECT_ADVANCED / CUB_PROJECT_LINESEARCH: its compile-time alternates
+                                 * USE_ADVANCED_PROJECTION (txx:340-397) and USE_LINESEARCH_PROJECTION
+                                 * (txx:398-438), h:22-23 - off in the reference, offered here at run time     */
+  int32_t  reserved;            /* must be 0                                                                  */
 } cub_params;
 
 /* Fills *p with the constructor defaults of txx:31-41

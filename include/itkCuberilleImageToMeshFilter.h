@@ -53,6 +53,15 @@
 
 #include "cuberille_c.h"
 
+// The reference selects its alternative projection schemes at compile time (h:22-23, all 0 by default); defining one
+// of them to 1 before including this header selects the same scheme here (cub_params.projection_method).
+#ifndef USE_ADVANCED_PROJECTION
+#define USE_ADVANCED_PROJECTION 0
+#endif
+#ifndef USE_LINESEARCH_PROJECTION
+#define USE_LINESEARCH_PROJECTION 0
+#endif
+
 namespace itk
 {
 
@@ -186,6 +195,11 @@ public:
   itkGetMacro( Device, int );
   itkSetMacro( Device, int );
 
+  /** Which ProjectVertexToIsoSurface scheme runs: CUB_PROJECT_DEFAULT (txx:440-474), CUB_PROJECT_ADVANCED (txx:340-397)
+   * or CUB_PROJECT_LINESEARCH (txx:398-438).  The default follows the reference's compile-time switches. */
+  itkGetMacro( ProjectionMethod, int );
+  itkSetMacro( ProjectionMethod, int );
+
   /** Page-lock the input image buffer while GenerateData() runs (cudaHostRegister), default off.  Speeds up the
    * host -> device copy of large images; registering costs time of its own. */
   itkGetMacro( PinInputBuffer, bool );
@@ -215,6 +229,8 @@ protected:
     m_Device = 0;
     m_Handle = 0;
     m_PinInputBuffer = false;
+    m_ProjectionMethod = USE_ADVANCED_PROJECTION ? CUB_PROJECT_ADVANCED
+                       : ( USE_LINESEARCH_PROJECTION ? CUB_PROJECT_LINESEARCH : CUB_PROJECT_DEFAULT );
     for ( int i = 0; i < 5; i++ ) { m_LastTimings[i] = 0.0; }
     for ( int i = 0; i < 3; i++ ) { m_Staging[i] = 0; m_StagingBytes[i] = 0; }
     }
@@ -305,6 +321,7 @@ protected:
     params.step_length = m_ProjectVertexStepLength;
     params.step_relaxation = m_ProjectVertexStepLengthRelaxationFactor;
     params.max_steps = m_ProjectVertexMaximumNumberOfSteps;
+    params.projection_method = m_ProjectionMethod;
 
     // PointIdentifier is unsigned long (64 bits), but a mesh of one handle has fewer than 2^32 points (cub_count
     // refuses more): the ids travel as 32-bit values - half the bytes over PCIe - and are widened when the cells
@@ -412,6 +429,7 @@ private:
   int                 m_Device;
   cub_handle          m_Handle;
   bool                m_PinInputBuffer;
+  int                 m_ProjectionMethod;
   double              m_LastTimings[5];
   void *              m_Staging[3];
   uint64_t            m_StagingBytes[3];

@@ -16,6 +16,7 @@ U8, I8, U16, I16, U32, I32, F32, F64 = range(8)
 MEM_HOST, MEM_DEVICE = 0, 1
 GEN_GYROID, GEN_MARSCHNER_LOBB, GEN_BLOBS = 0, 1, 2
 ORDER_REFERENCE, ORDER_RASTER = 0, 1
+PROJECT_DEFAULT, PROJECT_ADVANCED, PROJECT_LINESEARCH = 0, 1, 2
 
 DTYPE_CODES = {
     np.dtype(np.uint8): U8, np.dtype(np.int8): I8, np.dtype(np.uint16): U16, np.dtype(np.int16): I16,
@@ -49,6 +50,8 @@ class Params(C.Structure):
         ("step_relaxation", C.c_double),
         ("max_steps", C.c_uint32),
         ("image_border_faces", C.c_uint32),
+        ("projection_method", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 

@@ -348,7 +348,13 @@ int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool incl
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
   const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)h->num_sms * h->knobs.proj_ctas);
-  if (h->geom.oriented) { DISPATCH_PIXEL(h->dtype, (k_project<T, true><<<blocks, 128, 0, h->stream>>>(a))); }
+  const int method = h->params.projection_method;
+  if (method != CUB_PROJECT_DEFAULT) {
+    // the reference's compile-time alternates (USE_ADVANCED_PROJECTION / USE_LINESEARCH_PROJECTION)
+    const unsigned ablocks = (unsigned)std::min<size_t>(want, (size_t)h->num_sms * 16);
+    if (h->geom.oriented) { DISPATCH_PIXEL(h->dtype, (k_project_alt<T, true><<<ablocks, 128, 0, h->stream>>>(a, method))); }
+    else { DISPATCH_PIXEL(h->dtype, (k_project_alt<T, false><<<ablocks, 128, 0, h->stream>>>(a, method))); }
+  } else if (h->geom.oriented) { DISPATCH_PIXEL(h->dtype, (k_project<T, true><<<blocks, 128, 0, h->stream>>>(a))); }
   else { DISPATCH_PIXEL(h->dtype, (k_project<T, false><<<blocks, 128, 0, h->stream>>>(a))); }
   h->launches++;
   CU_TRY(h, cudaGetLastError());
@@ -599,6 +605,8 @@ int count_launch(cub_handle h, const cub_params* p) {
   CUB_TRY(setup_grid(h));
   if (iso_as_pixel(h->dtype, p->iso_value) != p->iso_value)
     return fail(h, CUB_ERR_INVALID, "iso value %.17g is not representable in the pixel type", p->iso_value);
+  if (p->projection_method < CUB_PROJECT_DEFAULT || p->projection_method > CUB_PROJECT_LINESEARCH || p->reserved != 0)
+    return fail(h, CUB_ERR_INVALID, "unknown projection_method %d", (int)p->projection_method);
   compute_step(h);
   const Grid& g = h->g;
   // the halo contract (cub_set_slab checks it too; cub_generate_volume with a z offset does not go through it)

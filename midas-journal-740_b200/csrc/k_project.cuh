@@ -322,4 +322,170 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   }
 }
 
+// ---- the reference's compile-time alternates (h:22-23): USE_ADVANCED_PROJECTION txx:340-397 and
+// USE_LINESEARCH_PROJECTION txx:398-438.  No test of the reference enables them; they are offered at run time
+// (cub_params.projection_method), one thread per vertex, with the same interpolation arithmetic as the default
+// branch (general clamped path, no cell cache: these variants are not the hot configuration), bit-identical to
+// oracle/cuberille_oracle.cpp::project_vertex_advanced / project_vertex_linesearch.
+enum { kProjectDefault = 0, kProjectAdvanced = 1, kProjectLineSearch = 2 };
+
+template <typename T, bool ORIENTED>
+struct Sampler {
+  VolView<T> v;
+  const ProjArgs& a;
+  float gc[3];
+  double inv_sp[3];
+  __device__ __forceinline__ Sampler(const ProjArgs& a_) : v{static_cast<const T*>(a_.vol), a_.g.X, a_.g.Y, a_.g.Zl, a_.g.zg0, a_.g.Zg}, a(a_) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      inv_sp[k] = 1.0 / a.geom.spacing[k];
+      gc[k] = (float)(0.5 * inv_sp[k]);
+    }
+  }
+  // interpolated value and (optionally) gradient at a Point<float>: ITK 3.x N-d linear interpolation (Appendix A.4)
+  template <bool GRAD>
+  __device__ __forceinline__ double sample(const float pt[3], double gd[3]) const {
+    double ci[3];
+    if (!ORIENTED) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ci[k] = ((double)pt[k] - a.geom.origin[k]) * inv_sp[k];
+    } else {
+      double c[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c[k] = (double)pt[k] - a.geom.origin[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sum += a.geom.minv[3 * i + j] * c[j];
+        ci[i] = sum;
+      }
+    }
+    long long base[3];
+    double dist[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double f = floor(ci[k]);
+      base[k] = (long long)f - a.i0[k];
+      dist[k] = ci[k] - f;
+    }
+    double value = 0.0, total = 0.0;
+    if (GRAD) gd[0] = gd[1] = gd[2] = 0.0;
+#pragma unroll 1
+    for (int counter = 0; counter < 8; ++counter) {
+      double overlap = 1.0;
+      overlap *= (counter & 1) ? dist[0] : 1.0 - dist[0];
+      overlap *= (counter & 2) ? dist[1] : 1.0 - dist[1];
+      overlap *= (counter & 4) ? dist[2] : 1.0 - dist[2];
+      if (overlap != 0.0) {
+        const int cx = clampi(base[0] + ((counter & 1) ? 1 : 0), v.X - 1);
+        const int cy = clampi(base[1] + ((counter & 2) ? 1 : 0), v.Y - 1);
+        const int cz = clampi(base[2] + ((counter & 4) ? 1 : 0), v.Zg - 1);
+        if (GRAD) {
+          float g[3];
+          gradient_at(v, gc, cx, cy, cz, g);
+          if (ORIENTED) rotate_gradient(a.geom, g);
+          gd[0] += overlap * (double)g[0];
+          gd[1] += overlap * (double)g[1];
+          gd[2] += overlap * (double)g[2];
+        } else {
+          value += overlap * (double)v.at(cx, cy, cz);
+        }
+        total += overlap;
+      }
+      if (total == 1.0) break;
+    }
+    return value;
+  }
+  // normal = gradient interpolated at the vertex, normalised (txx:351-352); false: zero gradient
+  __device__ __forceinline__ bool unit_normal(const float vertex[3], float normal[3]) const {
+    double gd[3];
+    sample<true>(vertex, gd);
+    double sq = 0.0;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      normal[k] = (float)gd[k];
+      const double c = (double)normal[k];
+      sq += c * c;
+    }
+    const double norm = sqrt(sq);
+    if (norm == 0.0) return false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+    return true;
+  }
+  __device__ __forceinline__ double value_at(const float pt[3]) const { return sample<false>(pt, nullptr); }
+};
+
+template <typename T, bool ORIENTED>
+__global__ void __launch_bounds__(128) k_project_alt(const ProjArgs a, int method) {
+  const Sampler<T, ORIENTED> S(a);
+  size_t n_points = a.n_points;
+  float* const points = a.points + (a.info && !a.include_ghost ? 3 * (size_t)__ldg(a.info + kInfoGhostV) : 0);
+  if (a.info) {
+    if (a.guard && !emission_fits(a.info)) return;
+    const size_t ghost = (size_t)__ldg(a.info + kInfoGhostV);
+    const size_t all = ghost + (size_t)__ldg(a.info + kInfoPoints);
+    n_points = a.include_ghost ? all : all - ghost;
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_points; i += (size_t)gridDim.x * blockDim.x) {
+    float vertex[3] = {points[3 * i], points[3 * i + 1], points[3 * i + 2]};
+    if (method == kProjectAdvanced) {
+      // txx:340-397
+      bool done = false;
+      double step = a.step0;
+      unsigned numberOfSteps = 0, swaps = 0;
+      int previousi = -1;
+      while (!done) {
+        float normal[3];
+        if (!S.unit_normal(vertex, normal)) break;
+        float t0[3], t1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          t0[k] = (float)((double)vertex[k] + ((double)normal[k] * +1.0) * step);
+          t1[k] = (float)((double)vertex[k] + ((double)normal[k] * -1.0) * step);
+        }
+        step *= a.relax;
+        const double d0 = fabs(S.value_at(t0) - a.iso), d1 = fabs(S.value_at(t1) - a.iso);
+        const int side = (d0 <= d1) ? 0 : 1;
+        if (previousi < 0) previousi = side;
+        swaps += (unsigned)(previousi != side);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) vertex[k] = side ? t1[k] : t0[k];
+        done |= (side ? d1 : d0) < a.thr;
+        if (done) break;
+        done |= numberOfSteps++ > a.max_steps;
+        if (done) break;
+        done |= swaps >= 5;
+      }
+    } else {
+      // txx:398-438
+      float normal[3];
+      if (S.unit_normal(vertex, normal)) {
+        float best[3] = {vertex[0], vertex[1], vertex[2]};
+        double bestMetric = 10000;
+        const unsigned half = a.max_steps / 2;
+        for (int s = 0; s < 2; ++s) {
+          const double sign = s == 0 ? -1.0 : 1.0;
+          for (unsigned j = 1; j < half; ++j) {
+            const double d = (double)j / ((double)a.max_steps / 2.0);
+            float temp[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) temp[k] = (float)((double)vertex[k] + (((double)normal[k] * sign) * a.step0) * d);
+            const double metric = fabs(S.value_at(temp) - a.iso);
+            if (metric < bestMetric) {
+              bestMetric = metric;
+              best[0] = temp[0]; best[1] = temp[1]; best[2] = temp[2];
+            }
+          }
+        }
+        vertex[0] = best[0]; vertex[1] = best[1]; vertex[2] = best[2];
+      }
+    }
+    points[3 * i] = vertex[0];
+    points[3 * i + 1] = vertex[1];
+    points[3 * i + 2] = vertex[2];
+  }
+}
+
 }  // namespace cbr

@@ -52,6 +52,7 @@ class CuberilleImageToMeshFilter:
         self._cell_data = False
         self._raster_order = False
         self._border_faces = False
+        self._projection_method = capi.PROJECT_DEFAULT
         self._thr = 0.5
         self._step = -1.0
         self._relax = 0.95
@@ -100,6 +101,9 @@ class CuberilleImageToMeshFilter:
     # extension: number the vertices in lattice-corner raster order instead of the reference's creation order
     def SetImageBorderFaces(self, b): self._set("_border_faces", bool(b))   # opt-in closed mesh (txx:133 TODO)
     def GetImageBorderFaces(self): return self._border_faces
+    # the reference's compile-time alternates USE_ADVANCED_PROJECTION / USE_LINESEARCH_PROJECTION (h:22-23), at run time
+    def SetProjectionMethod(self, m): self._set("_projection_method", int(m))
+    def GetProjectionMethod(self): return self._projection_method
     def SetRasterVertexOrder(self, b): self._set("_raster_order", bool(b))
     def GetRasterVertexOrder(self): return self._raster_order
 
@@ -132,6 +136,7 @@ class CuberilleImageToMeshFilter:
         p.step_length = self._step
         p.step_relaxation = self._relax
         p.max_steps = self._max_steps
+        p.projection_method = self._projection_method
         return p
 
     def Update(self):

@@ -70,6 +70,9 @@ struct orc_params {
   int64_t region_index[3];      // image index of the buffer's first voxel (ImageRegion::GetIndex; the tests of the
                                 // reference only have 0): TransformIndexToPhysicalPoint sees index + region_index
   double direction[9];          // row-major direction cosines; all zero or the identity: a non-oriented image
+  int32_t projection_method;    // 0: the default branch (txx:440-474); 1: USE_ADVANCED_PROJECTION (txx:340-397);
+                                // 2: USE_LINESEARCH_PROJECTION (txx:398-438) - compile-time alternates of the reference (h:22-23)
+  int32_t reserved;
 };
 
 struct orc_mesh {
@@ -281,6 +284,96 @@ inline void project_vertex(const Volume<T>& v, const orc_params& P, double step0
   }
 }
 
+// normal = m_GradientInterpolator->Evaluate(vertex); normal.Normalize();  (txx:351-352, 411-412, 451-452)
+// false: zero gradient (the reference would divide by zero)
+template <typename T>
+inline bool unit_normal(const Volume<T>& v, const float vertex[3], float normal[3]) {
+  const double p[3] = {(double)vertex[0], (double)vertex[1], (double)vertex[2]};
+  double gd[3];
+  interp_gradient(v, p, gd);
+  for (int k = 0; k < 3; ++k) normal[k] = (float)gd[k];  // CovariantVector<float,3>
+  double sq = 0.0;
+  for (int k = 0; k < 3; ++k) {
+    const double c = (double)normal[k];
+    sq += c * c;
+  }
+  const double norm = std::sqrt(sq);
+  if (norm == 0.0) return false;
+  for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+  return true;
+}
+
+template <typename T>
+inline double value_at(const Volume<T>& v, const float pt[3]) {
+  const double p[3] = {(double)pt[0], (double)pt[1], (double)pt[2]};
+  return interp_scalar(v, p);
+}
+
+// ProjectVertexToIsoSurface, USE_ADVANCED_PROJECTION branch (txx:340-397): step both ways along the normal, keep the
+// side whose value is closer to the iso value, stop on the threshold, the step count or five changes of side.
+template <typename T>
+inline void project_vertex_advanced(const Volume<T>& v, const orc_params& P, double step0, float vertex[3]) {
+  bool done = false;
+  double step = step0;
+  unsigned numberOfSteps = 0;
+  const double iso = (double)(T)P.iso_value;
+  unsigned swaps = 0;
+  int previousi = -1;
+  while (!done) {
+    float normal[3];
+    if (!unit_normal(v, vertex, normal)) break;  // (same policy as the default branch)
+    float temp[2][3];
+    for (int i = 0; i < 3; ++i) {  // txx:355-359: float = float + (float * double * double)
+      temp[0][i] = (float)((double)vertex[i] + ((double)normal[i] * +1.0) * step);
+      temp[1][i] = (float)((double)vertex[i] + ((double)normal[i] * -1.0) * step);
+    }
+    step *= P.step_relaxation;  // txx:360
+    const double diff[2] = {std::fabs(value_at(v, temp[0]) - iso), std::fabs(value_at(v, temp[1]) - iso)};  // txx:363-366
+    const int i = (diff[0] <= diff[1]) ? 0 : 1;  // txx:367
+    if (previousi < 0) previousi = i;
+    swaps += (unsigned)(previousi != i);  // txx:369 (previousi is never updated in the reference)
+    for (int k = 0; k < 3; ++k) vertex[k] = temp[i][k];
+    done |= diff[i] < P.surface_distance_threshold;  // txx:373
+    if (done) break;
+    done |= numberOfSteps++ > P.max_steps;  // txx:380
+    if (done) break;
+    done |= (swaps >= 5);  // txx:387
+  }
+}
+
+// ProjectVertexToIsoSurface, USE_LINESEARCH_PROJECTION branch (txx:398-438): one normal, max_steps/2 - 1 samples on
+// either side within one step length, keep the sample whose value is closest to the iso value.
+template <typename T>
+inline void project_vertex_linesearch(const Volume<T>& v, const orc_params& P, double step0, float vertex[3]) {
+  const double iso = (double)(T)P.iso_value;
+  float normal[3];
+  if (!unit_normal(v, vertex, normal)) return;
+  float best[3] = {vertex[0], vertex[1], vertex[2]};  // (bestVertex is uninitialised in the reference if no sample improves on 10000)
+  double bestMetric = 10000;
+  const unsigned half = P.max_steps / 2;  // txx:418, integer division
+  for (int side = 0; side < 2; ++side) {
+    const double sign = side == 0 ? -1.0 : 1.0;  // txx:415
+    for (unsigned j = 1; j < half; ++j) {
+      const double d = (double)j / ((double)P.max_steps / 2.0);  // txx:421
+      float temp[3];
+      for (int i = 0; i < 3; ++i) temp[i] = (float)((double)vertex[i] + (((double)normal[i] * sign) * step0) * d);  // txx:424
+      const double metric = std::fabs(value_at(v, temp) - iso);  // txx:427-428
+      if (metric < bestMetric) {
+        bestMetric = metric;
+        best[0] = temp[0]; best[1] = temp[1]; best[2] = temp[2];
+      }
+    }
+  }
+  vertex[0] = best[0]; vertex[1] = best[1]; vertex[2] = best[2];
+}
+
+template <typename T>
+inline void project_any(const Volume<T>& v, const orc_params& P, double step0, float vertex[3]) {
+  if (P.projection_method == 1) project_vertex_advanced(v, P, step0, vertex);
+  else if (P.projection_method == 2) project_vertex_linesearch(v, P, step0, vertex);
+  else project_vertex(v, P, step0, vertex);
+}
+
 // AddVertex without the projection (txx:265-270; SURVEY Appendix A.2, ITK 3.x form).
 inline void corner_position(const Geometry& g, int64_t cx, int64_t cy, int64_t cz, float out[3]) {
   const int64_t idx[3] = {cx, cy, cz};
@@ -321,7 +414,7 @@ struct Runner {
   void add_vertex(int64_t cx, int64_t cy, int64_t cz) {  // txx:257-276
     float v[3];
     corner_position(vol.g, cx, cy, cz, v);
-    if (P.project_vertices) project_vertex(vol, P, step0, v);
+    if (P.project_vertices) project_any(vol, P, step0, v);
     mesh->points.insert(mesh->points.end(), v, v + 3);
   }
 
@@ -509,7 +602,7 @@ void project_typed(const void* data, const Geometry& g, const orc_params& P, flo
   double maxSpacing = g.spacing[0];
   for (int a = 1; a < 3; ++a) maxSpacing = g.spacing[a] > maxSpacing ? g.spacing[a] : maxSpacing;
   const double step0 = P.step_length < 0.0 ? maxSpacing * 0.25 : P.step_length;
-  for (uint64_t i = 0; i < n; ++i) project_vertex(v, P, step0, pts + 3 * i);
+  for (uint64_t i = 0; i < n; ++i) project_any(v, P, step0, pts + 3 * i);
 }
 
 template <typename T>

@@ -23,6 +23,7 @@ DTYPE_CODES = {
 
 LITERAL = 0
 CLOSED_FORM = 1
+PROJECT_DEFAULT, PROJECT_ADVANCED, PROJECT_LINESEARCH = 0, 1, 2
 
 
 class _Params(C.Structure):
@@ -39,6 +40,8 @@ class _Params(C.Structure):
         ("image_border_faces", C.c_uint32),
         ("region_index", C.c_int64 * 3),
         ("direction", C.c_double * 9),
+        ("projection_method", C.c_int32),
+        ("reserved", C.c_int32),
     ]
 
 
@@ -101,20 +104,20 @@ def _geom(vol: np.ndarray, spacing, origin):
 
 
 def _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces=False,
-            region_index=(0, 0, 0), direction=None) -> _Params:
+            region_index=(0, 0, 0), direction=None, method=0) -> _Params:
     d = [float(v) for v in np.asarray(direction, np.float64).reshape(9)] if direction is not None else [0.0] * 9
     return _Params(float(iso), int(bool(triangles)), int(bool(project)), int(bool(cell_data)), int(mode),
                    float(thr), float(step), float(relax), int(max_steps), int(bool(border_faces)),
-                   (C.c_int64 * 3)(*[int(v) for v in region_index]), (C.c_double * 9)(*d))
+                   (C.c_int64 * 3)(*[int(v) for v in region_index]), (C.c_double * 9)(*d), int(method), 0)
 
 
 def cuberille(vol: np.ndarray, iso, *, triangles=True, project=True, cell_data=False, mode=LITERAL,
               thr=0.5, step=-1.0, relax=0.95, max_steps=50, spacing=None, origin=None, border_faces=False,
-              region_index=(0, 0, 0), direction=None) -> Mesh:
+              region_index=(0, 0, 0), direction=None, method=0) -> Mesh:
     """Run the oracle.  `vol` is indexed [z, y, x] (x fastest), like a MetaImage buffer."""
     L = lib()
     dims, sp, og = _geom(vol, spacing, origin)
-    P = _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces, region_index, direction)
+    P = _params(iso, triangles, project, cell_data, mode, thr, step, relax, max_steps, border_faces, region_index, direction, method)
     h = L.orc_cuberille(vol.ctypes.data, DTYPE_CODES[vol.dtype], dims, sp, og, C.byref(P))
     if not h:
         raise RuntimeError("oracle: unsupported dtype")
@@ -154,10 +157,10 @@ def classify(vol: np.ndarray, iso, words_per_row: int | None = None) -> np.ndarr
 
 
 def project_points(vol: np.ndarray, iso, pts: np.ndarray, *, thr=0.5, step=-1.0, relax=0.95, max_steps=50,
-                   spacing=None, origin=None, direction=None) -> np.ndarray:
+                   spacing=None, origin=None, direction=None, method=0) -> np.ndarray:
     L = lib()
     dims, sp, og = _geom(vol, spacing, origin)
-    P = _params(iso, True, True, False, LITERAL, thr, step, relax, max_steps, direction=direction)
+    P = _params(iso, True, True, False, LITERAL, thr, step, relax, max_steps, direction=direction, method=method)
     out = np.ascontiguousarray(pts, np.float32).copy()
     L.orc_project_points(vol.ctypes.data, DTYPE_CODES[vol.dtype], dims, sp, og, C.byref(P), out.ctypes.data,
                          out.shape[0])

@@ -18,7 +18,7 @@ def test_library_builds_and_exports_every_declared_symbol():
     assert declared == set(P.capi.SYMBOLS), declared ^ set(P.capi.SYMBOLS)
     for s in declared:
         assert hasattr(L, s), f"{s} not exported"
-    assert L.cub_abi_version() == 2
+    assert L.cub_abi_version() == 3
 
 
 def test_default_params_are_the_reference_constructor_defaults():

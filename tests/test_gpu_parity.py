@@ -580,3 +580,60 @@ def test_generated_slab_without_set_slab_is_refused():
     h.set_slab(64, 20, 22, 35)
     h.count(p)
     h.close()
+
+
+# ---- the reference's compile-time alternates of ProjectVertexToIsoSurface --------------------------
+@pytest.mark.parametrize("method", [1, 2], ids=["advanced", "linesearch"])
+@pytest.mark.parametrize("fixture,iso,max_steps", [("fuel", 15, 100), ("neghip", 55, 100), ("nucleon", 140, 100), ("marschnerlobb", 55, 40)])
+def test_alternate_projections_on_reference_fixtures(method, fixture, iso, max_steps):
+    """USE_ADVANCED_PROJECTION (txx:340-397) / USE_LINESEARCH_PROJECTION (txx:398-438) as run-time variants: points and the
+    projected triangle split bit-exact against the oracle's restatement of the same branches"""
+    O = oracle()
+    img = read_fixture(fixture)
+    kw = dict(triangles=True, project=True, thr=0.2, step=0.24, relax=0.95, max_steps=max_steps)
+    ref = O.cuberille(img.data, iso, method=method, **kw)
+    mesh = run_filter(img, iso, method=method, **kw)
+    assert_mesh_equal(mesh, ref, f"{fixture} method {method}")
+    plain = O.cuberille(img.data, iso, **kw)
+    assert not np.array_equal(plain.points, ref.points)   # (the variants do move the vertices differently)
+
+
+@pytest.mark.parametrize("method", [1, 2], ids=["advanced", "linesearch"])
+def test_alternate_projections_float_anisotropic_oriented_and_slabs(method):
+    O, P = oracle(), pkg()
+    vol, iso = smooth_volume((36, 20, 44), np.float32, seed=77)
+    sp, og, D = (0.5, 1.25, 2.0), (3.0, -2.0, 7.0), DIRECTIONS["rot_z_30"]
+    kw = dict(triangles=True, project=True, thr=0.02, step=0.3, relax=0.9, max_steps=30)
+    ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, spacing=sp, origin=og, direction=D, method=method, **kw)
+    mesh = run_filter(P.Image(vol, sp, og, D), iso, method=method, **kw)
+    assert_mesh_equal(mesh, ref, f"oriented method {method}")
+    # z-slabs (isotropic, non-oriented): the halo rule of the default branch covers both variants
+    ref2 = O.cuberille(vol, iso, mode=O.CLOSED_FORM, method=method, **kw)
+    prm = P.capi.default_params()
+    prm.iso_value, prm.generate_triangles, prm.project_vertices, prm.projection_method = float(iso), 1, 1, method
+    prm.surface_distance_threshold, prm.step_length, prm.step_relaxation, prm.max_steps = 0.02, 0.3, 0.9, 30
+    halo = max(P.capi.projection_halo(prm))
+    pts, cells, pb, cb = [], [], 0, 0
+    for s in P.slabs.plan_slabs(vol.shape[0], 3, halo):
+        h = P.capi.Handle(0)
+        h.set_volume(vol[s.local_z0:s.local_z1])
+        h.set_slab(vol.shape[0], s.local_z0, s.own_z0, s.own_z1)
+        a, b = h.count(prm)
+        h.set_id_base(pb, cb)
+        h.emit(4)
+        x, y, _ = h.fetch()
+        pts.append(x); cells.append(y)
+        pb += a; cb += 2 * b
+        h.close()
+    assert_mesh_equal(P.Mesh(np.concatenate(pts), np.concatenate(cells)), ref2, f"slabs method {method}")
+
+
+def test_unknown_projection_method_is_refused():
+    P = pkg()
+    h = P.capi.Handle(0)
+    h.set_volume(np.zeros((4, 4, 4), np.uint8))
+    p = P.capi.default_params()
+    p.projection_method = 7
+    with pytest.raises(P.capi.CuberilleError):
+        h.count(p)
+    h.close()

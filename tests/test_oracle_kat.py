@@ -154,7 +154,7 @@ def test_oracle_params_struct_layout():
     body = body[:body.index("};")]
     names = re.findall(r"^\s*(?:double|int32_t|uint32_t|int64_t)\s+(\w+)", body, re.M)
     assert names == [n for n, _ in O._Params._fields_]
-    assert C.sizeof(O._Params) == 8 + 4 * 4 + 3 * 8 + 2 * 4 + 3 * 8 + 9 * 8
+    assert C.sizeof(O._Params) == 8 + 4 * 4 + 3 * 8 + 2 * 4 + 3 * 8 + 9 * 8 + 2 * 4
 
 
 # ---- oriented images: the oracle's restatement of ITK's direction-matrix semantics ---------------
@@ -200,3 +200,19 @@ def test_oracle_axis_permutation_is_equivariant():
     b = O.cuberille(vol, iso, direction=D.reshape(9), **kw)
     assert np.array_equal(a.cells, b.cells)
     assert np.array_equal(b.points.view(np.uint32), (a.points @ D.T.astype(np.float32)).view(np.uint32))
+
+
+@pytest.mark.parametrize("method", [1, 2])
+def test_oracle_alternate_projections_keep_counts_and_move_towards_the_surface(method):
+    """USE_ADVANCED_PROJECTION / USE_LINESEARCH_PROJECTION (txx:340-438): same counts and connectivity classes as the
+    default branch (projection never changes counts); the vertices end closer to the iso value than they started"""
+    O = oracle()
+    img = read_fixture("fuel")
+    kw = dict(thr=0.2, step=0.24, relax=0.95, max_steps=100)
+    flat = O.cuberille(img.data, 15, triangles=False, project=False)
+    m = O.cuberille(img.data, 15, triangles=False, project=True, method=method, **kw)
+    assert m.points.shape == flat.points.shape == (5302, 3) and np.array_equal(m.cells, flat.cells)
+    v0, _ = O.sample(img.data, flat.points.astype(np.float64))
+    v1, _ = O.sample(img.data, m.points.astype(np.float64))
+    assert np.abs(v1 - 15).mean() < 0.5 * np.abs(v0 - 15).mean()
+    assert np.isfinite(m.points).all()

@@ -103,7 +103,7 @@ def smooth_volume(shape, dtype, seed, scale=60.0):
 
 
 def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5, step=-1.0, relax=0.95, max_steps=50,
-               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), raster_order=False, border_faces=False):
+               id_bytes=4, spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0), raster_order=False, border_faces=False, method=0):
     """Drive the CUDA path through the filter mirror, with the reference driver's call sequence
     (Testing/CuberilleTest01.cxx:144-162)."""
     P = pkg()
@@ -116,6 +116,7 @@ def run_filter(img_or_vol, iso, *, triangles, project, cell_data=False, thr=0.5,
     f.SetSavePixelAsCellData(cell_data)
     f.SetRasterVertexOrder(raster_order)
     f.SetImageBorderFaces(border_faces)
+    f.SetProjectionMethod(method)
     f.SetProjectVertexSurfaceDistanceThreshold(thr)
     if step >= 0:
         f.SetProjectVertexStepLength(step)

@@ -39,8 +39,9 @@ while time.time() - t0 < budget:
         geo["direction"] = tuple(float(x) for x in Dm.reshape(9))
         raster = False  # (the raster-order check sorts by physical coordinates)
     ridx = tuple(int(x) for x in rng.integers(-4, 5, 3)) if rng.random() < 0.3 else (0, 0, 0)
-    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} {geo}"
-    kw = dict(triangles=tri, project=proj, cell_data=cd, thr=0.02)
+    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} method={method} {geo}"
+    method = int(rng.choice([0, 0, 1, 2])) if proj else 0   # the reference's alternative projection branches (txx:340-438)
+    kw = dict(triangles=tri, project=proj, cell_data=cd, thr=0.02, method=method)
     ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, border_faces=border, region_index=ridx, **kw, **geo)
     img = P.Image(vol, geo["spacing"], geo["origin"]); img.region_index = ridx
     if "direction" in geo:
@@ -65,6 +66,7 @@ while time.time() - t0 < budget:
                 prm = P.capi.default_params()
                 prm.iso_value, prm.generate_triangles, prm.project_vertices = float(iso), int(tri), int(proj)
                 prm.save_pixel_as_cell_data, prm.image_border_faces, prm.surface_distance_threshold = int(cd), int(border), 0.02
+                prm.projection_method = method
                 pts, cells, cds, pb, cb = [], [], [], 0, 0
                 # a projected vertex travels up to step / (1 - relax) = 5 * max spacing, i.e. many slices when the z
                 # spacing is the small one: give the slabs the whole image as halo then
@@ -94,6 +96,7 @@ while time.time() - t0 < budget:
                 prm = P.capi.default_params()
                 prm.iso_value, prm.generate_triangles, prm.project_vertices = float(iso), int(tri), int(proj)
                 prm.image_border_faces, prm.surface_distance_threshold = int(border), 0.02
+                prm.projection_method = method
                 kw2 = {}
                 if resident:
                     sts = [torch.cuda.Stream() for _ in range(n_h)]
