@@ -34,6 +34,18 @@ def test_driver_compiles_and_fails_loudly_without_a_gpu(tmp_path):
     assert "ExceptionObject caught" in r.stderr and "no usable CUDA device" in r.stderr
 
 
+def test_adapter_instantiates_for_every_pixel_type_and_exports_the_reference_typedefs(tmp_path):
+    """compile + link + run (no GPU needed: nothing calls Update()) of tests/cpp/adapter_instantiations.cxx"""
+    pkg().build()
+    exe = str(tmp_path / "inst")
+    subprocess.check_call(["g++", "-O0", "-std=c++17", "-Wall", "-Wextra", "-Wno-unused-parameter", "-Wno-unused-local-typedefs",
+                           "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "itk_shim"),
+                           os.path.join(CPP, "adapter_instantiations.cxx"), "-o", exe,
+                           "-L", os.path.dirname(pkg().capi.lib_path()), "-lcuberille_cuda",
+                           "-Wl,-rpath," + os.path.dirname(pkg().capi.lib_path())])
+    assert subprocess.run([exe]).returncode == 0
+
+
 def test_driver_usage_message(tmp_path):
     build_driver()
     r = subprocess.run([EXE], capture_output=True, text=True)
