@@ -39,8 +39,8 @@ while time.time() - t0 < budget:
         geo["direction"] = tuple(float(x) for x in Dm.reshape(9))
         raster = False  # (the raster-order check sorts by physical coordinates)
     ridx = tuple(int(x) for x in rng.integers(-4, 5, 3)) if rng.random() < 0.3 else (0, 0, 0)
-    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} method={method} {geo}"
     method = int(rng.choice([0, 0, 1, 2])) if proj else 0   # the reference's alternative projection branches (txx:340-438)
+    what = f"#{n} {np.dtype(dt).name} {shape} smooth={smooth} tri={tri} proj={proj} cd={cd} border={border} raster={raster} ids={idb} ridx={ridx} method={method} {geo}"
     kw = dict(triangles=tri, project=proj, cell_data=cd, thr=0.02, method=method)
     ref = O.cuberille(vol, iso, mode=O.CLOSED_FORM, border_faces=border, region_index=ridx, **kw, **geo)
     img = P.Image(vol, geo["spacing"], geo["origin"]); img.region_index = ridx
