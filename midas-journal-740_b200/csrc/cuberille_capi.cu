@@ -37,6 +37,7 @@ struct Knobs {
   int count_cfg = -1;        // CUB_COUNT_CFG: sweep tile configuration (-1: by row length)
   int k1_packed = 1;         // CUB_K1_PACKED: 4-bytes-per-lane classify for 8/16-bit pixels
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
+  int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
   int proj_ctas = 5;         // CUB_PROJ_CTAS_PER_SM
 };
 
@@ -443,6 +444,7 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.count_cfg = env_int("CUB_COUNT_CFG", -1, -1, 10);
     h->knobs.k1_packed = env_int("CUB_K1_PACKED", 1, 0, 1);
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
+    h->knobs.scan_rows = env_int("CUB_SCAN_ROWS", 1, 0, 1);
     h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
   }
   bool ok = ensure(h, h->ctrl, kCtrlHead) == CUB_OK &&
@@ -676,12 +678,16 @@ int count_launch(cub_handle h, const cub_params* p) {
   // K2 scan range = voxel slices [owner_z_min, zs1) and corner planes [zs0, zs1]
   const size_t row_begin = (size_t)h->owner_z_min * h->EY;
   const size_t n_rows = (size_t)(h->zs1 + 1 - h->owner_z_min) * h->EY;
-  // one large scan tile per resident CTA, so that every tile is in flight when the look-backs run
+  // one large scan tile per resident CTA, so that every tile is in flight when the look-backs run; rows with at most
+  // two segments take the one-pass kernel, whose warps hold at most 32 * kScanBatches rows (more tiles than resident
+  // CTAs are fine: a tile only waits for tiles with earlier tickets)
   int scan_occ = 0;
   CU_TRY(h, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&scan_occ, k_seg_scan, kScanThreads, 0));
   const size_t max_tiles = (size_t)h->num_sms * std::max(1, std::min(scan_occ, h->knobs.scan_ctas));
   size_t rows_per_tile = ((n_rows + max_tiles - 1) / max_tiles + kScanWarps - 1) / kScanWarps * kScanWarps;
   if (rows_per_tile < (size_t)kScanWarps) rows_per_tile = kScanWarps;
+  const bool scan_rows = h->NS <= 2 && h->knobs.scan_rows;
+  if (scan_rows) rows_per_tile = std::min<size_t>(rows_per_tile, (size_t)kScanWarps * 32 * kScanBatches);
   const size_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
   {
     const size_t need = kCtrlHead + 3 * n_tiles + ((size_t)g.Zl + 2 + 1) / 2;
@@ -724,7 +730,9 @@ int count_launch(cub_handle h, const cub_params* p) {
     sa.mark_row_c = (h->own_z0 > 0) ? (unsigned)((size_t)(h->zs0 + 1) * h->EY) : 0xffffffffu;
     sa.rows_per_tile = (unsigned)rows_per_tile; sa.n_tiles = (unsigned)n_tiles;
     sa.status = h->d_status; sa.ticket = h->d_ticket; sa.info = h->d_info;
-    k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
+    if (scan_rows && h->NS == 1) k_seg_scan_rows<1><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
+    else if (scan_rows) k_seg_scan_rows<2><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
+    else k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
     k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->d_slice_any, h->owner_z_min, h->zs1);

@@ -238,6 +238,105 @@ __global__ void __launch_bounds__(kScanThreads) k_seg_scan(const SegScanArgs a) 
   }
 }
 
+// The common case - at most two segments per lattice row (EW <= 64, i.e. X <= 1983) and at most 128 rows per warp -
+// in ONE pass over the counts: a lane owns a row, a warp 32 rows at a time, up to four such batches; the row totals
+// (and, for the second segment, the sum of the row's first 32 entries) stay in registers while the CTA aggregate
+// goes through the look-back, then warp scans over the rows give every row's prefix and the lane writes its one or
+// two segment bases.  Every count is read exactly once (the general kernel above reads them three times: 0.088 ms
+// against 0.05 ms for the 151 MB of a 1024^3 lattice).
+constexpr int kScanBatches = 4;
+
+template <int NS>
+__global__ void __launch_bounds__(kScanThreads) k_seg_scan_rows(const SegScanArgs a) {
+  __shared__ unsigned int s_tile;
+  __shared__ unsigned long long s_part[3][kScanWarps];
+  __shared__ unsigned long long s_excl[3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+  __syncthreads();
+  const unsigned tile = s_tile;
+  if (tile >= a.n_tiles) return;
+  const unsigned rpw = a.rows_per_tile / kScanWarps;   // <= 32 * kScanBatches
+  const unsigned r0 = min(tile * a.rows_per_tile + warp * rpw, a.n_rows);
+  const unsigned r1 = min(r0 + rpw, a.n_rows);
+  const unsigned ew4 = a.EW / 4;
+
+  uint32_t tv[kScanBatches], tf[kScanBatches], tc[kScanBatches], pv[kScanBatches], pf[kScanBatches], pc[kScanBatches];
+#pragma unroll
+  for (int b = 0; b < kScanBatches; ++b) {
+    tv[b] = tf[b] = tc[b] = pv[b] = pf[b] = pc[b] = 0;
+    const unsigned r = r0 + 32 * b + lane;
+    if (r < r1) {
+      const unsigned row = a.row_begin + r;
+      const uint4* __restrict__ p = reinterpret_cast<const uint4*>(a.cnt + (size_t)row * a.EW);
+      uint32_t v = 0, f = 0, c = 0;
+      for (unsigned k = 0; k < ew4; ++k) {
+        if (NS == 2 && k == 8) { pv[b] = v; pf[b] = f; pc[b] = c; }   // the second segment starts at entry 32
+        const uint4 q = __ldg(p + k);
+        v += (q.x & 0x3ffu) + (q.y & 0x3ffu) + (q.z & 0x3ffu) + (q.w & 0x3ffu);
+        f += ((q.x >> 10) & 0x3ffu) + ((q.y >> 10) & 0x3ffu) + ((q.z >> 10) & 0x3ffu) + ((q.w >> 10) & 0x3ffu);
+        c += (q.x >> 20) + (q.y >> 20) + (q.z >> 20) + (q.w >> 20);
+      }
+      const bool counted = row >= a.ghost_row_end;
+      tv[b] = v; tf[b] = f; tc[b] = counted ? c : 0u;
+      if (!counted) pc[b] = 0;
+    }
+  }
+  // warp aggregate -> CTA aggregate -> look-back
+  unsigned long long sv = 0, sf = 0, sc = 0;
+#pragma unroll
+  for (int b = 0; b < kScanBatches; ++b) { sv += tv[b]; sf += tf[b]; sc += tc[b]; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    sv += __shfl_xor_sync(0xffffffffu, sv, o);
+    sf += __shfl_xor_sync(0xffffffffu, sf, o);
+    sc += __shfl_xor_sync(0xffffffffu, sc, o);
+  }
+  if (lane == 0) { s_part[0][warp] = sv; s_part[1][warp] = sf; s_part[2][warp] = sc; }
+  __syncthreads();
+  if (warp < 3) {
+    const int k = warp;
+    unsigned long long aggk = 0;
+#pragma unroll
+    for (int i = 0; i < kScanWarps; ++i) aggk += s_part[k][i];
+    unsigned long long* st = a.status + (size_t)k * a.n_tiles;
+    if (lane == 0) st_relaxed(st + tile, (tile == 0 ? kFlagPrefix : kFlagAggregate) | aggk);
+    unsigned long long ex = 0;
+    if (tile > 0) {
+      ex = lookback(st, (int)tile, lane);
+      if (lane == 0) st_relaxed(st + tile, kFlagPrefix | (ex + aggk));
+    }
+    if (lane == 0) {
+      s_excl[k] = ex;
+      if (tile == a.n_tiles - 1) a.info[kInfoTotV + k] = ex + aggk;
+    }
+  }
+  __syncthreads();
+  unsigned long long run_v = s_excl[0], run_f = s_excl[1], run_c = s_excl[2];
+  for (int i = 0; i < warp; ++i) { run_v += s_part[0][i]; run_f += s_part[1][i]; run_c += s_part[2][i]; }
+  uint32_t v = (uint32_t)run_v, f = (uint32_t)run_f, c = (uint32_t)run_c;
+#pragma unroll
+  for (int b = 0; b < kScanBatches; ++b) {
+    uint32_t iv = tv[b], jf = tf[b], ic = tc[b];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t x = __shfl_up_sync(0xffffffffu, iv, o), y = __shfl_up_sync(0xffffffffu, jf, o), z = __shfl_up_sync(0xffffffffu, ic, o);
+      if (lane >= o) { iv += x; jf += y; ic += z; }
+    }
+    const unsigned r = r0 + 32 * b + lane;
+    if (r < r1) {
+      const unsigned row = a.row_begin + r;
+      const uint32_t bv = v + iv - tv[b], bf = f + jf - tf[b], bc = c + ic - tc[b];  // prefix at the start of the lane's row
+      if (row == a.mark_row_vf) { a.info[kInfoMarkV] = bv; a.info[kInfoMarkF] = bf; }
+      if (row == a.mark_row_c) a.info[kInfoMarkC] = bc;
+      uint4* __restrict__ out = a.seg + (size_t)row * NS;
+      out[0] = make_uint4(bv, bf, bc, 0u);
+      if (NS == 2) out[1] = make_uint4(bv + pv[b], bf + pf[b], bc + pc[b], 0u);
+    }
+    v += __shfl_sync(0xffffffffu, iv, 31); f += __shfl_sync(0xffffffffu, jf, 31); c += __shfl_sync(0xffffffffu, ic, 31);
+  }
+}
+
 // Derived counts of the run: what the own range produces, the default id bases, and the empty-interior-slice check.
 //   raster != 0: vertex ids are corner slots (CUB_ORDER_RASTER)
 //   slice_any[z] != 0: voxel slice z of the scanned range has an inside voxel (set by k_sweep)

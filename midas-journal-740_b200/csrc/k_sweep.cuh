@@ -52,9 +52,7 @@ struct SweepCfg {
   static constexpr int NT = NTX * NTY;               // live threads
   static constexpr int NTP = (NT + 31) / 32 * 32;    // launched threads
   static constexpr int NW = NTP / 32;
-  // resident CTAs the register allocation aims at: the (17, 7, 2) tile needs 6 x 128 threads per SM to hide its load
-  // chain (r1: 80 registers; the slice-occupancy flag of r2 pushed it to 88 = 5 CTAs, 376 -> 389 us)
-  static constexpr int MINB = 1;  // (forcing 6 CTAs = 80 registers was measured: 388 -> 404 us)
+  static constexpr int MINB = (NTP == 128 && R_ == 2) ? 5 : 1;  // (forcing 6 CTAs/SM = 80 registers on the (17, 7, 2) tile was measured in r2: 388 -> 404 us)
   static constexpr int LO = 0;
   static constexpr int CR = NTY * R;                 // corner rows per CTA
   static constexpr int TXW = NTX - 1 - 2 * LO;       // voxel words (x) whose results the CTA produces
@@ -174,6 +172,7 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     act_prev[k] = 0;
   }
 
+  uint32_t occupied = 0;  // bit k: voxel slice zs + k has an inside voxel in this thread's words (a.tz <= 32)
   for (int cz = zs; cz <= ze; ++cz) {
     const int buf = cz & 1;
     // ---- 1. slide the window, decode slice cz (fetched during the previous step), closed form for plane cz ---
@@ -220,13 +219,16 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
       exw[4 * NT] = lo_c[1];
       exw[5 * NT] = nib;
     }
-    // (the barrier also tells whether slice cz-1 has an inside voxel at all: the empty-interior-slice check)
-    uint32_t any_in = 0;
+    // does slice cz-1 have an inside voxel at all (the empty-interior-slice check)?  One bit per slice of the CTA's
+    // sweep in a per-thread mask, reduced and stored once after the sweep.
+    {
+      uint32_t any_in = 0;
 #pragma unroll
-    for (int k = 0; k < R; ++k)
-      if ((rowok_bits >> k) & 1u) any_in |= lo_c[k + 1] & vc;
-    const int slice_occupied = __syncthreads_or(any_in != 0);
-    if (t == 0 && slice_occupied && cz > zs && a.slice_any) a.slice_any[cz - 1] = 1u;
+      for (int k = 0; k < R; ++k)
+        if ((rowok_bits >> k) & 1u) any_in |= lo_c[k + 1] & vc;
+      if (any_in != 0 && cz > zs) occupied |= 1u << (cz - 1 - zs);
+    }
+    __syncthreads();
 
     uint32_t act[R];
 #pragma unroll
@@ -315,6 +317,11 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     }
     su4 = p4u; su5 = p5u;
     nr_prev = nr; nur_prev = nur;
+  }
+  if (a.slice_any) {
+    occupied = __reduce_or_sync(0xffffffffu, occupied);
+    const int lane = t & 31;
+    if (((occupied >> lane) & 1u) && zs + lane < ze) a.slice_any[zs + lane] = 1u;
   }
 }
 
