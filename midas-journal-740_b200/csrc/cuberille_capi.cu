@@ -50,7 +50,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 
 // slices per CTA sweep: long sweeps amortise the warm-up planes, but the grid must still fill the GPU
 int pick_tz(int gx, int gy, int nz, int num_sms) {
-  int tz = 64;   // (k_sweep keeps one occupancy bit per slice of a sweep in a 64-bit mask)
+  int tz = 32;
   while (tz > 4 && (long long)gx * gy * ((nz + tz - 1) / tz) < 6LL * num_sms) tz >>= 1;
   if (tz > nz) tz = nz;
   return tz < 1 ? 1 : tz;
@@ -730,13 +730,14 @@ int count_launch(cub_handle h, const cub_params* p) {
     sa.mark_row_c = (h->own_z0 > 0) ? (unsigned)((size_t)(h->zs0 + 1) * h->EY) : 0xffffffffu;
     sa.rows_per_tile = (unsigned)rows_per_tile; sa.n_tiles = (unsigned)n_tiles;
     sa.status = h->d_status; sa.ticket = h->d_ticket; sa.info = h->d_info;
-    sa.raster = h->raster ? 1 : 0; sa.slice_any = h->d_slice_any; sa.z_begin = h->owner_z_min; sa.z_end = h->zs1;
     if (scan_rows && h->NS == 1) k_seg_scan_rows<1><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     else if (scan_rows) k_seg_scan_rows<2><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     else k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
     h->launches++;
     CU_TRY(h, cudaGetLastError());
-    // (the derived counts - finalize_info - are written by the scan tile that finishes last)
+    k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->d_slice_any, h->owner_z_min, h->zs1);
+    h->launches++;
+    CU_TRY(h, cudaGetLastError());
     if (h->timing) {
       cudaEventRecord(h->ev[1], h->stream);
       cudaEventSynchronize(h->ev[1]);

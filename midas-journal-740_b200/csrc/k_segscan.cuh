@@ -86,12 +86,8 @@ struct SegScanArgs {
   unsigned rows_per_tile;        // a multiple of kScanWarps
   unsigned n_tiles;
   unsigned long long* status;    // [3][n_tiles] descriptors
-  unsigned int* ticket;          // [0] tile tickets, [1] finished tiles
+  unsigned int* ticket;
   unsigned long long* info;      // kInfo* slots
-  // finalize_info, run by the last tile
-  int raster;
-  const uint32_t* slice_any;
-  int z_begin, z_end;
 };
 
 __device__ __forceinline__ unsigned long long ld_relaxed(const unsigned long long* p) {
@@ -124,53 +120,6 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long*
     pos -= 32;
   }
   return exclusive;
-}
-
-// Derived counts of the run (finalize_info): what the own range produces, the default id bases, and the empty-interior-slice check.
-//   raster != 0: vertex ids are corner slots (CUB_ORDER_RASTER)
-//   slice_any[z] != 0: voxel slice z of the scanned range has an inside voxel (set by k_sweep)
-// An empty voxel slice between two occupied ones: the reference's lookup-plane rotation (txx:155-161) only
-// advances on inside voxels, so it merges vertices of different corner planes there (SURVEY section 8a row 3);
-// this library implements the intended rule and reports the case through cub_last_warning.
-// Executed by the scan tile that finishes LAST (a counter of finished tiles), with all its threads: no launch of its own.
-__device__ __forceinline__ void finalize_info(volatile unsigned long long* info, int raster, const volatile uint32_t* slice_any,
-                                              int z_begin, int z_end) {
-  __shared__ int s_first, s_last, s_hole;
-  if (threadIdx.x == 0) { s_first = INT_MAX; s_last = -1; s_hole = 0; }
-  __syncthreads();
-  if (slice_any) {
-    int first = INT_MAX, last = -1;
-    for (int z = z_begin + (int)threadIdx.x; z < z_end; z += (int)blockDim.x)
-      if (slice_any[z]) { first = min(first, z); last = max(last, z); }
-    if (last >= 0) { atomicMin(&s_first, first); atomicMax(&s_last, last); }
-    __syncthreads();
-    for (int z = z_begin + (int)threadIdx.x; z < z_end; z += (int)blockDim.x)
-      if (z > s_first && z < s_last && !slice_any[z]) s_hole = 1;
-    __syncthreads();
-  }
-  if (threadIdx.x != 0) return;
-  const unsigned long long ghost_v = raster ? info[kInfoMarkC] : info[kInfoMarkV];
-  info[kInfoGhostV] = ghost_v;
-  info[kInfoPoints] = (raster ? info[kInfoTotC] : info[kInfoTotV]) - ghost_v;
-  info[kInfoQuads] = info[kInfoTotF] - info[kInfoMarkF];
-  info[kInfoPointBase] = 0;
-  info[kInfoCellBase] = 0;
-  info[kInfoIdDelta] = 0ull - ghost_v;
-  info[kInfoFlags] = s_hole ? (unsigned long long)kFlagEmptyInteriorSlice : 0ull;
-  info[kInfoWork] = 0;
-  info[kInfoSplitWork] = 0;
-}
-
-// the last tile to finish runs finalize_info: every tile publishes its writes (fence) and counts itself
-__device__ __forceinline__ void scan_tile_done(const SegScanArgs& a) {
-  __shared__ unsigned int s_done;
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_done = atomicAdd(a.ticket + 1, 1u);
-  __syncthreads();
-  if (s_done != a.n_tiles - 1) return;
-  __threadfence();
-  finalize_info(a.info, a.raster, a.slice_any, a.z_begin, a.z_end);
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_seg_scan(const SegScanArgs a) {
@@ -287,7 +236,6 @@ __global__ void __launch_bounds__(kScanThreads) k_seg_scan(const SegScanArgs a) 
     }
     v += __shfl_sync(0xffffffffu, iv, 31); f += __shfl_sync(0xffffffffu, jf, 31); c += __shfl_sync(0xffffffffu, ic, 31);
   }
-  scan_tile_done(a);
 }
 
 // The common case - at most two segments per lattice row (EW <= 64, i.e. X <= 1983) and at most 128 rows per warp -
@@ -387,7 +335,40 @@ __global__ void __launch_bounds__(kScanThreads) k_seg_scan_rows(const SegScanArg
     }
     v += __shfl_sync(0xffffffffu, iv, 31); f += __shfl_sync(0xffffffffu, jf, 31); c += __shfl_sync(0xffffffffu, ic, 31);
   }
-  scan_tile_done(a);
+}
+
+// Derived counts of the run: what the own range produces, the default id bases, and the empty-interior-slice check.
+//   raster != 0: vertex ids are corner slots (CUB_ORDER_RASTER)
+//   slice_any[z] != 0: voxel slice z of the scanned range has an inside voxel (set by k_sweep)
+// An empty voxel slice between two occupied ones: the reference's lookup-plane rotation (txx:155-161) only
+// advances on inside voxels, so it merges vertices of different corner planes there (SURVEY section 8a row 3);
+// this library implements the intended rule and reports the case through cub_last_warning.
+__global__ void __launch_bounds__(256) k_finalize_info(unsigned long long* info, int raster, const uint32_t* slice_any,
+                                                       int z_begin, int z_end) {
+  __shared__ int s_first, s_last, s_hole;
+  if (threadIdx.x == 0) { s_first = INT_MAX; s_last = -1; s_hole = 0; }
+  __syncthreads();
+  if (slice_any) {
+    int first = INT_MAX, last = -1;
+    for (int z = z_begin + (int)threadIdx.x; z < z_end; z += (int)blockDim.x)
+      if (slice_any[z]) { first = min(first, z); last = max(last, z); }
+    if (last >= 0) { atomicMin(&s_first, first); atomicMax(&s_last, last); }
+    __syncthreads();
+    for (int z = z_begin + (int)threadIdx.x; z < z_end; z += (int)blockDim.x)
+      if (z > s_first && z < s_last && !slice_any[z]) s_hole = 1;
+    __syncthreads();
+  }
+  if (threadIdx.x != 0) return;
+  const unsigned long long ghost_v = raster ? info[kInfoMarkC] : info[kInfoMarkV];
+  info[kInfoGhostV] = ghost_v;
+  info[kInfoPoints] = (raster ? info[kInfoTotC] : info[kInfoTotV]) - ghost_v;
+  info[kInfoQuads] = info[kInfoTotF] - info[kInfoMarkF];
+  info[kInfoPointBase] = 0;
+  info[kInfoCellBase] = 0;
+  info[kInfoIdDelta] = 0ull - ghost_v;
+  info[kInfoFlags] = s_hole ? (unsigned long long)kFlagEmptyInteriorSlice : 0ull;
+  info[kInfoWork] = 0;
+  info[kInfoSplitWork] = 0;
 }
 
 __global__ void k_set_bases(unsigned long long* info, unsigned long long point_base, unsigned long long cell_base) {

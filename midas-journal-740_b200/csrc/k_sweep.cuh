@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     act_prev[k] = 0;
   }
 
-  unsigned long long occupied = 0;  // bit k: voxel slice zs + k has an inside voxel in this thread's words (a.tz <= 64)
+  uint32_t occupied = 0;  // bit k: voxel slice zs + k has an inside voxel in this thread's words (a.tz <= 32)
   for (int cz = zs; cz <= ze; ++cz) {
     const int buf = cz & 1;
     // ---- 1. slide the window, decode slice cz (fetched during the previous step), closed form for plane cz ---
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
 #pragma unroll
       for (int k = 0; k < R; ++k)
         if ((rowok_bits >> k) & 1u) any_in |= lo_c[k + 1] & vc;
-      if (any_in != 0 && cz > zs) occupied |= 1ull << (cz - 1 - zs);
+      if (any_in != 0 && cz > zs) occupied |= 1u << (cz - 1 - zs);
     }
     __syncthreads();
 
@@ -319,10 +319,9 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     nr_prev = nr; nur_prev = nur;
   }
   if (a.slice_any) {
-    const uint32_t lo = __reduce_or_sync(0xffffffffu, (uint32_t)occupied), hi = __reduce_or_sync(0xffffffffu, (uint32_t)(occupied >> 32));
+    occupied = __reduce_or_sync(0xffffffffu, occupied);
     const int lane = t & 31;
-    if (((lo >> lane) & 1u) && zs + lane < ze) a.slice_any[zs + lane] = 1u;
-    if (((hi >> lane) & 1u) && zs + 32 + lane < ze) a.slice_any[zs + 32 + lane] = 1u;
+    if (((occupied >> lane) & 1u) && zs + lane < ze) a.slice_any[zs + lane] = 1u;
   }
 }
 
