@@ -358,16 +358,18 @@ def main():
     own_vox = S * S * (own1 - own0)
     local_vox = S * S * (hi - lo)
     alg_k1 = local_vox * 4  # K1 reads every voxel of the local buffer once
-    k1_gbs = alg_k1 / (kavg["classify"] * 1e-3) / 1e9
+    fused = h.count_was_fused()  # K1 + K2a ran as one kernel: "classify" is that kernel, "count_scan" the scan alone
+    k1_gbs = alg_k1 / (max(kavg["classify"], 1e-6) * 1e-3) / 1e9
     alg_pipe = own_vox * 4 + n_pts * 12 + n_quads * 16
     cc_ms = kavg["classify"] + kavg["count_scan"]
     traffic = None
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("k_classify_dram_bytes_per_launch")
+            traffic = json.load(f).get("k_classify_sweep_dram_bytes_per_launch" if fused else "k_classify_dram_bytes_per_launch")
     except Exception:
         pass
-    roofline = {"bound": "hbm", "kernel": "k_classify<float>", "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k_classify_sweep<float> (classification + ownership sweep, fused)" if fused else "k_classify<float>",
+                "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                 "frac": k1_gbs / peak, "traffic": traffic if N == 1 and S == 1024 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_k1, "avg_launch_ms": kavg["classify"],
                 "kernel_ms": kavg,

@@ -325,6 +325,11 @@ int cub_get_timings(cub_handle h, float ms[8]);
 /* Number of kernel launches issued by this handle so far.                      */
 uint64_t cub_launch_count(cub_handle h);
 
+/* 1 if the last cub_count ran classification + ownership sweep as the one fused
+ * kernel (k_classify_sweep; [0] of cub_get_timings is then that kernel and [1]
+ * the scan alone), 0 if it ran them as two kernels.  Diagnostic only.           */
+int cub_count_was_fused(cub_handle h);
+
 int cub_abi_version(void);
 
 #ifdef __cplusplus

@@ -30,7 +30,7 @@ SYMBOLS = [
     "cub_set_region_index", "cub_set_slab", "cub_count", "cub_set_id_base", "cub_emit_vertices", "cub_emit", "cub_run", "cub_fetch", "cub_fetch_async",
     "cub_synchronize", "cub_device_buffers",
     "cub_debug_bitmask", "cub_debug_project_points", "cub_generate_volume", "cub_download_volume",
-    "cub_enable_timing", "cub_get_timings", "cub_launch_count",
+    "cub_enable_timing", "cub_get_timings", "cub_launch_count", "cub_count_was_fused",
     "cub_projection_halo", "cub_count_async", "cub_device_counts", "cub_emit_async", "cub_finish", "cub_last_warning",
     "cub_comm_unique_id", "cub_comm_create", "cub_comm_destroy", "cub_comm_exchange_counts", "cub_comm_counts",
     "cub_comm_gather_mesh", "cub_device_alloc", "cub_device_free", "cub_device_copy",
@@ -125,6 +125,8 @@ def load() -> C.CDLL:
     L.cub_get_timings.argtypes = [vp, C.POINTER(C.c_float)]
     L.cub_launch_count.restype = u64
     L.cub_launch_count.argtypes = [vp]
+    L.cub_count_was_fused.restype = i
+    L.cub_count_was_fused.argtypes = [vp]
     L.cub_projection_halo.restype = i
     L.cub_projection_halo.argtypes = [C.POINTER(Params), pd, pu64, pu64]
     L.cub_count_async.restype = i
@@ -346,6 +348,10 @@ class Handle:
 
     def launch_count(self) -> int:
         return int(self._L.cub_launch_count(self._h))
+
+    def count_was_fused(self) -> bool:
+        """True if the last count ran classification + sweep as the one fused kernel (k_fused.cuh)."""
+        return bool(self._L.cub_count_was_fused(self._h))
 
 
 def comm_unique_id() -> bytes:

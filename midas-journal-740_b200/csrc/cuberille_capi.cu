@@ -26,6 +26,7 @@
 #include "k_faces.cuh"
 #include "k_project.cuh"
 #include "k_sweep.cuh"
+#include "k_fused.cuh"
 #include "k_vertices.cuh"
 
 using namespace cbr;
@@ -36,6 +37,11 @@ namespace {
 struct Knobs {
   int count_cfg = -1;        // CUB_COUNT_CFG: sweep tile configuration (-1: by row length)
   int k1_packed = 1;         // CUB_K1_PACKED: 4-bytes-per-lane classify for 8/16-bit pixels
+  int k1_ctas = 32;          // CUB_K1_CTAS_PER_SM: grid cap of the classification kernel
+  int fuse = 1;              // CUB_FUSE: classification + ownership sweep in one warp-specialised kernel (k_fused.cuh)
+  int fuse_tz = 0;           // CUB_FUSE_TZ: slices per sweep tile of the fused kernel (0: pick_tz)
+  int fuse_ctas = 4;         // CUB_FUSE_CTAS_PER_SM
+  int fuse_dbg = 0;          // CUB_FUSE_DBG: timing experiments (results are wrong): 1 = no sweep, 2 = no classification
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
   int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
   int proj_ctas = 5;         // CUB_PROJ_CTAS_PER_SM
@@ -116,6 +122,9 @@ struct cub_handle_s {
   // one control block, cleared with ONE memset per count: [info (kInfoWords + 2) | ticket | status (3 x tiles) | slice_any]
   DevBuf<unsigned long long> ctrl;
   uint32_t* d_slice_any = nullptr;
+  unsigned* d_fuse_done = nullptr;
+  unsigned* d_fuse_ctr = nullptr;
+  bool fused_last = false;     // the last count ran K1 + K2a as the fused kernel
   unsigned long long* d_status = nullptr;
   DevBuf<uint32_t> vtx;      // K3a -> K3b: the lattice corner of every vertex id
   DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
@@ -315,6 +324,68 @@ void launch_classify(cub_handle h, int z0, int z1, cudaStream_t stream, int ctas
     k_classify<T, false><<<(unsigned)blocks, 256, 0, stream>>>(vol, bits, g, (T)h->params.iso_value, tasks, groups);
 }
 
+// K1 + K2a as one kernel (k_fused.cuh).  Returns false (nothing launched) where the fused kernel does not apply: the
+// caller then runs the two kernels one after the other.
+constexpr int kFuseStages = 3;
+
+template <typename T, typename C>
+bool launch_fused_cfg(cub_handle h, const SweepArgs& ca, unsigned* ctr, unsigned* done) {
+  using Smem = FuseSmem<C, kFuseStages>;
+  constexpr int WPT = kFuseStageBytes / (32 * (int)sizeof(T));
+  const Grid& g = ca.g;
+  FuseArgs fa{};
+  fa.sw = ca;
+  fa.vol = h->d_vol;
+  fa.bits = h->bits.p;
+  fa.groups_per_row = (unsigned)((g.Wx + WPT - 1) / WPT);
+  fa.tasks_per_slice = fa.groups_per_row * (unsigned)g.Y;
+  const unsigned long long tasks = (unsigned long long)fa.tasks_per_slice * (unsigned long long)g.Zl;
+  if (tasks >= (1ull << 32) - kFuseBatch) return false;
+  fa.n_tasks = (unsigned)tasks;
+  fa.n_batches = (unsigned)((tasks + kFuseBatch - 1) / kFuseBatch);
+  const int gx = (g.Wx + C::TXW - 1) / C::TXW, gy = (g.Y + C::TY - 1) / C::TY;
+  const int nz = ca.z_end - ca.z_begin;
+  // short sweeps: a tile can only start when the slice above its last one is classified, and what is still to sweep
+  // when the producers finish is the kernel's tail; the two warm-up planes per tile cost issue slots the kernel has
+  fa.sw.tz = std::min(h->knobs.fuse_tz > 0 ? h->knobs.fuse_tz : 8, pick_tz(gx, gy, nz, h->num_sms));
+  const unsigned long long tiles = (unsigned long long)gx * gy * ((nz + fa.sw.tz - 1) / fa.sw.tz);
+  if (tiles >= (1ull << 31)) return false;
+  fa.n_tiles = (unsigned)tiles; fa.gx = (unsigned)gx; fa.gy = (unsigned)gy;
+  fa.ctr = ctr; fa.done = done;
+  fa.dbg = h->knobs.fuse_dbg;
+  auto kern = k_classify_sweep<T, C, kFuseStages>;
+  static bool attr_set = false;  // (per instantiation; the attribute is per device function and idempotent)
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
+      cudaGetLastError();
+      return false;
+    }
+    attr_set = true;
+  }
+  // persistent: every CTA resident (4 per SM: 64 registers x 256 threads, ~47 KB of shared memory)
+  const unsigned long long want = std::max<unsigned long long>((fa.n_batches + 3) / 4, fa.n_tiles);
+  const unsigned blocks = (unsigned)std::max<unsigned long long>(1, std::min<unsigned long long>(want, (unsigned long long)h->num_sms * h->knobs.fuse_ctas));
+  kern<<<blocks, kFuseThreads, sizeof(Smem), h->stream>>>(fa, (T)h->params.iso_value);
+  h->launches++;
+  return true;
+}
+
+template <typename T>
+bool launch_fused(cub_handle h, const SweepArgs& ca, int cfg, unsigned* ctr, unsigned* done) {
+  if (!h->knobs.fuse || h->pad) return false;
+  const Grid& g = ca.g;
+  // 8- and 16-bit pixels keep their own classification kernel (4 pixels per lane per load) where it applies
+  if (is_packable<T>::value && h->knobs.k1_packed && g.X % (32 * (4 / (int)sizeof(T))) == 0 &&
+      (reinterpret_cast<uintptr_t>(h->d_vol) & 3u) == 0)
+    return false;
+  // TMA bulk copies: 16-byte aligned rows
+  if (((size_t)g.X * sizeof(T)) % 16 != 0 || (reinterpret_cast<uintptr_t>(h->d_vol) & 15u) != 0) return false;
+  const int c = cfg >= 0 ? cfg : (g.Wx > 8 ? 2 : 10);
+  if (c == 2) return launch_fused_cfg<T, SweepCfg<17, 7, 2, MODE_COUNT>>(h, ca, ctr, done);
+  if (c == 10) return launch_fused_cfg<T, SweepCfg<9, 14, 2, MODE_COUNT>>(h, ca, ctr, done);
+  return false;
+}
+
 // K4 on `pts` (explicit count n), or - from_info - on the handle's point buffer with the range taken from the
 // device-side run info (n = the capacity of the buffer)
 Caps make_caps(cub_handle h, unsigned long long quads_cap) {
@@ -443,6 +514,11 @@ int cub_create(int device, void* stream, cub_handle* out) {
     // the tuning knobs are read here, once, and clamped (a zero would make a launch with no blocks)
     h->knobs.count_cfg = env_int("CUB_COUNT_CFG", -1, -1, 10);
     h->knobs.k1_packed = env_int("CUB_K1_PACKED", 1, 0, 1);
+    h->knobs.k1_ctas = env_int("CUB_K1_CTAS_PER_SM", 32, 1, 32);
+    h->knobs.fuse = env_int("CUB_FUSE", 1, 0, 1);
+    h->knobs.fuse_tz = env_int("CUB_FUSE_TZ", 0, 0, 32);
+    h->knobs.fuse_ctas = env_int("CUB_FUSE_CTAS_PER_SM", 4, 1, 4);
+    h->knobs.fuse_dbg = env_int("CUB_FUSE_DBG", 0, 0, 3);
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
     h->knobs.scan_rows = env_int("CUB_SCAN_ROWS", 1, 0, 1);
     h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
@@ -690,12 +766,15 @@ int count_launch(cub_handle h, const cub_params* p) {
   if (scan_rows) rows_per_tile = std::min<size_t>(rows_per_tile, (size_t)kScanWarps * 32 * kScanBatches);
   const size_t n_tiles = (n_rows + rows_per_tile - 1) / rows_per_tile;
   {
-    const size_t need = kCtrlHead + 3 * n_tiles + ((size_t)g.Zl + 2 + 1) / 2;
+    const size_t slice_words = ((size_t)g.Zl + 2 + 1) / 2;  // one u32 per slice
+    const size_t need = kCtrlHead + 3 * n_tiles + 2 * slice_words + 1;
     CUB_TRY(ensure(h, h->ctrl, need));
     h->d_info = h->ctrl.p;
     h->d_ticket = reinterpret_cast<unsigned int*>(h->ctrl.p + kInfoWords + 2);
     h->d_status = h->ctrl.p + kCtrlHead;
     h->d_slice_any = reinterpret_cast<uint32_t*>(h->d_status + 3 * n_tiles);
+    h->d_fuse_done = reinterpret_cast<unsigned*>(h->d_status + 3 * n_tiles + slice_words);   // fused kernel: tasks done per slice
+    h->d_fuse_ctr = reinterpret_cast<unsigned*>(h->d_status + 3 * n_tiles + 2 * slice_words);  // ... and its two tickets
     h->ctrl_used = need;
   }
   SweepArgs ca{};
@@ -703,19 +782,27 @@ int count_launch(cub_handle h, const cub_params* p) {
   ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = h->raster ? nullptr : h->own.p;
   ca.slice_any = h->d_slice_any;
   {
-    // K1 then K2a on the handle's stream.  (Running the HBM-bound K1 beside the issue-bound K2a, on two streams by
-    // z-chunks or even without any dependency, was measured in r1 and took K1 + K2a: DESIGN.md section 8.)
+    // K1 + K2a: one warp-specialised kernel where it applies (k_fused.cuh), else K1 then K2a on the handle's stream.
+    // The control block (tickets, per-slice progress, scan descriptors, slice occupancy) is cleared first.
+    CU_TRY(h, cudaMemsetAsync(h->ctrl.p, 0, h->ctrl_used * sizeof(unsigned long long), h->stream));
+    ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
+    bool fused = false;
     {
       Timer t(h, 0);
-      DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, 0, g.Zl, h->stream, 32));
+      DISPATCH_PIXEL(h->dtype, fused = launch_fused<T>(h, ca, h->knobs.count_cfg, h->d_fuse_ctr, h->d_fuse_done));
       CU_TRY(h, cudaGetLastError());
+      if (!fused) {
+        DISPATCH_PIXEL(h->dtype, launch_classify<T>(h, 0, g.Zl, h->stream, h->knobs.k1_ctas));
+        CU_TRY(h, cudaGetLastError());
+      }
       t.stop();
     }
-    CU_TRY(h, cudaMemsetAsync(h->ctrl.p, 0, h->ctrl_used * sizeof(unsigned long long), h->stream));
+    h->fused_last = fused;
     if (h->timing) cudaEventRecord(h->ev[0], h->stream);
-    ca.z_begin = h->owner_z_min; ca.z_end = h->zs1;
-    CU_TRY(h, dispatch_sweep(ca, h->stream, h->num_sms, h->knobs.count_cfg));
-    h->launches++;
+    if (!fused) {
+      CU_TRY(h, dispatch_sweep(ca, h->stream, h->num_sms, h->knobs.count_cfg));
+      h->launches++;
+    }
   }
   {
     if (h->timing) cudaEventRecord(h->ev[6], h->stream);
@@ -1315,6 +1402,7 @@ int cub_get_timings(cub_handle h, float ms[8]) {
 }
 
 uint64_t cub_launch_count(cub_handle h) { return h ? h->launches : 0; }
+int cub_count_was_fused(cub_handle h) { return (h && h->fused_last) ? 1 : 0; }
 
 }  // extern "C"
 

@@ -84,23 +84,22 @@ __device__ __forceinline__ void corner_owners(const uint32_t in[8], uint32_t vm,
   own[3] |= t2 & in[6] & ~in[7];
 }
 
-template <typename C>
-__global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
-  using S = SweepSmem<C>;
+// One tile of the sweep: thread t of the C::NTP threads that share `sm`, tile (bx, by) of the x-y plane, z chunk bz.
+// FUSED: the caller is one warpgroup of k_classify_sweep (k_fused.cuh) - the threads meet at named barrier 1 instead of
+// the CTA barrier, and the bitmask, written by other SMs earlier in the SAME kernel, is read past the (incoherent) L1.
+template <typename C, bool FUSED>
+__device__ __forceinline__ void sweep_tile(const SweepArgs& a, SweepSmem<C>& sm, const int t, const int bx, const int by,
+                                           const int bz) {
   constexpr int NTX = C::NTX, NTY = C::NTY, R = C::R, MODE = C::MODE, NT = C::NT, CR = C::CR;
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  S& sm = *reinterpret_cast<S*>(smem_raw);
-
   const Grid& g = a.g;
-  const int t = threadIdx.x;
   const bool alive = t < NT;
   const int tt = alive ? t : 0;
   const int i = tt % NTX, j = tt / NTX;
-  const int w0 = blockIdx.x * C::TXW, y0 = blockIdx.y * C::TY;
+  const int w0 = bx * C::TXW, y0 = by * C::TY;
   const int cw = w0 + i;
   const int rr0 = j * R;          // first corner row of the thread, CTA-relative
   const int cy0 = y0 + rr0;       // ... and in the image
-  const int zs = a.z_begin + blockIdx.z * a.tz;
+  const int zs = a.z_begin + bz * a.tz;
   const int ze = min(zs + a.tz, a.z_end);
 
   // ---- per-thread constants ---------------------------------------------------------------------------
@@ -140,8 +139,8 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     const uint32_t* __restrict__ sl = a.bits + (size_t)min(max(zl, zlo), zhi) * slice_words;
 #pragma unroll
     for (int k = 0; k <= R; ++k) {
-      cwv[k] = __ldg(sl + rowoff[k]);
-      pwv[k] = __ldg(sl + rowoff[k] - dprev);
+      cwv[k] = FUSED ? __ldcg(sl + rowoff[k]) : __ldg(sl + rowoff[k]);
+      pwv[k] = FUSED ? __ldcg(sl + rowoff[k] - dprev) : __ldg(sl + rowoff[k] - dprev);
     }
   };
   // -> c (voxel x = corner x) and l (voxel x-1) words, edge-replicated in x
@@ -228,7 +227,8 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
         if ((rowok_bits >> k) & 1u) any_in |= lo_c[k + 1] & vc;
       if (any_in != 0 && cz > zs) occupied |= 1u << (cz - 1 - zs);
     }
-    __syncthreads();
+    if (FUSED) asm volatile("bar.sync 1, %0;" ::"n"(C::NTP) : "memory");
+    else __syncthreads();
 
     uint32_t act[R];
 #pragma unroll
@@ -323,6 +323,13 @@ __global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
     const int lane = t & 31;
     if (((occupied >> lane) & 1u) && zs + lane < ze) a.slice_any[zs + lane] = 1u;
   }
+}
+
+template <typename C>
+__global__ void __launch_bounds__(C::NTP, C::MINB) k_sweep(const SweepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  sweep_tile<C, false>(a, *reinterpret_cast<SweepSmem<C>*>(smem_raw), (int)threadIdx.x, (int)blockIdx.x, (int)blockIdx.y,
+                       (int)blockIdx.z);
 }
 
 }  // namespace cbr
