@@ -45,6 +45,7 @@ struct Knobs {
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
   int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
   int proj_ctas = 5;         // CUB_PROJ_CTAS_PER_SM
+  int proj_refill = 18;      // CUB_PROJ_REFILL: lanes of a warp that keep iterating before the warp serves the idle ones
 };
 
 int env_int(const char* name, int dflt, int lo, int hi) {
@@ -417,6 +418,7 @@ int launch_project(cub_handle h, float* pts, size_t n, bool from_info, bool incl
   a.guard = guard ? 1 : 0;
   a.caps = make_caps(h, quads_cap);
   a.work = h->d_info + kInfoWords;
+  a.refill = (unsigned)h->knobs.proj_refill;
   CU_TRY(h, cudaMemsetAsync(a.work, 0, sizeof(unsigned long long), h->stream));
   const size_t want = (n + 127) / 128;
   const unsigned blocks = (unsigned)std::min<size_t>(want, (size_t)h->num_sms * h->knobs.proj_ctas);
@@ -522,6 +524,7 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
     h->knobs.scan_rows = env_int("CUB_SCAN_ROWS", 1, 0, 1);
     h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
+    h->knobs.proj_refill = env_int("CUB_PROJ_REFILL", 18, 1, 32);
   }
   bool ok = ensure(h, h->ctrl, kCtrlHead) == CUB_OK &&
             cudaMallocHost(&h->h_info, (kInfoWords + 2) * sizeof(unsigned long long)) == cudaSuccess;

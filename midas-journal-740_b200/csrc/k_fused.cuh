@@ -65,6 +65,7 @@ __device__ __forceinline__ void mbar_init(unsigned long long* b, unsigned count)
 __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, unsigned bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(b)), "r"(bytes) : "memory");
 }
+// (an L2 evict-first hint on these copies - the volume is read once - was measured: 0.88 -> 1.05 ms; plain copies it is)
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned bytes, unsigned long long* b) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
                "l"(src), "r"(bytes), "r"(smem_addr(b))

@@ -38,6 +38,7 @@ struct ProjArgs {
   Caps caps;
   long long i0[3];           // image index of buffer voxel (0, 0, 0) (cub_set_region_index): continuous indices are image indices
   unsigned long long* work;  // device counter (zeroed before the launch): next vertex to hand out
+  unsigned refill;           // lanes of a warp that must still be iterating for the warp to skip the service phase (1..32)
 };
 
 template <typename T>
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
     n_points = a.include_ghost ? all : all - ghost;
   }
   size_t i = 0;
-  bool have = false;
+  bool have = false, exhausted = false;
   float vert[3] = {0.f, 0.f, 0.f};
   double step = a.step0;
   unsigned numberOfSteps = 0;
@@ -135,46 +136,58 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   long long cell[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
   double nval[8];
   float ngrad[8][3];
+  // continuous index of `vert`: base index (buffer-relative) and distances (shared by both interpolators)
+  // (32-bit saturated base indices were measured in r2: same register count, 5.15 -> 5.33 ms)
+  long long base[3] = {0, 0, 0};
+  double dist[3] = {0.0, 0.0, 0.0};
+  auto locate = [&]() {
+    double ci[3];
+    if (!ORIENTED) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) ci[k] = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
+    } else {
+      // TransformPhysicalPointToContinuousIndex of an oriented image: M^-1 * (point - origin), row sums from 0
+      double c[3];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) c[k] = (double)vert[k] - a.geom.origin[k];
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) sum += a.geom.minv[3 * i + j] * c[j];
+        ci[i] = sum;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      const double f = floor(ci[k]);
+      base[k] = (long long)f - a.i0[k];  // buffer-relative
+      dist[k] = ci[k] - f;
+    }
+  };
 
+  // Two phases per round (the per-vertex arithmetic is the reference's loop body, unchanged):
+  //   SERVICE  lanes without a vertex take the next one from the global counter; lanes whose vertex is in a cell
+  //            other than the cached one (a new vertex, or one that crossed a cell face) load the cell
+  //   ITERATE  passes of the reference's `while ( !done )` body (txx:448-473) for the lanes whose cell is cached,
+  //            repeated while at least a.refill lanes of the warp still have one to make
+  // so that the long cell load runs for many lanes at a time instead of once per lane event (r1/r2: every pass of a
+  // warp went through it with one or two lanes active, and it took as many issue slots as the iterations).
   while (true) {
-    if (!have) {
+    if (!have && !exhausted) {
       i = (size_t)atomicAdd(a.work, 1ull);
-      if (i >= n_points) break;
-      vert[0] = points[3 * i]; vert[1] = points[3 * i + 1]; vert[2] = points[3 * i + 2];
-      step = a.step0;
-      numberOfSteps = 0;
-      have = true;
-    }
-    bool done = false;  // one pass of the reference's `while ( !done )` body (txx:448-473)
-    // continuous index, base index and distances (shared by both interpolators)
-    long long base[3];
-    double dist[3];
-    {
-      double ci[3];
-      if (!ORIENTED) {
-#pragma unroll
-        for (int k = 0; k < 3; ++k) ci[k] = ((double)vert[k] - a.geom.origin[k]) * inv_sp[k];
+      if (i >= n_points) {
+        exhausted = true;
       } else {
-        // TransformPhysicalPointToContinuousIndex of an oriented image: M^-1 * (point - origin), row sums from 0
-        double c[3];
-#pragma unroll
-        for (int k = 0; k < 3; ++k) c[k] = (double)vert[k] - a.geom.origin[k];
-#pragma unroll
-        for (int i = 0; i < 3; ++i) {
-          double sum = 0.0;
-#pragma unroll
-          for (int j = 0; j < 3; ++j) sum += a.geom.minv[3 * i + j] * c[j];
-          ci[i] = sum;
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < 3; ++k) {
-        const double f = floor(ci[k]);
-        base[k] = (long long)f - a.i0[k];  // buffer-relative
-        dist[k] = ci[k] - f;
+        vert[0] = points[3 * i]; vert[1] = points[3 * i + 1]; vert[2] = points[3 * i + 2];
+        step = a.step0;
+        numberOfSteps = 0;
+        have = true;
+        locate();
       }
     }
-    if (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2]) {
+    if (__all_sync(0xffffffffu, !have)) break;
+    if (have && (base[0] != cell[0] || base[1] != cell[1] || base[2] != cell[2])) {
       cell[0] = base[0]; cell[1] = base[1]; cell[2] = base[2];
       const long long zl0 = base[2] - v.zg0;  // local slice of node z = 0
       const bool nodes_inside = base[0] >= 0 && base[0] + 1 <= v.X - 1 && base[1] >= 0 && base[1] + 1 <= v.Y - 1 &&
@@ -248,77 +261,86 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
         }
       }
     }
-    double gd[3] = {0.0, 0.0, 0.0};
-    double value = 0.0, total = 0.0;
-    bool open = true;
-    // overlap = ((1 * wx) * wy) * wz in the reference's order; 1 * wx is wx, and the four wx * wy products are shared
-    // by the two z layers (same values, same association: bit-identical, 12 multiplications instead of 24)
-    const double wx[2] = {1.0 - dist[0], dist[0]}, wy[2] = {1.0 - dist[1], dist[1]}, wz[2] = {1.0 - dist[2], dist[2]};
-    const double wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
-#pragma unroll
-    for (int counter = 0; counter < 8; ++counter) {
-      if (open) {
-        const double overlap = wxy[counter & 3] * wz[counter >> 2];
-        if (overlap != 0.0) {
-          gd[0] += overlap * (double)ngrad[counter][0];
-          gd[1] += overlap * (double)ngrad[counter][1];
-          gd[2] += overlap * (double)ngrad[counter][2];
-          value += overlap * nval[counter];
-          total += overlap;
+    unsigned n_active;
+    do {
+      if (have && base[0] == cell[0] && base[1] == cell[1] && base[2] == cell[2]) {
+        bool done = false;  // one pass of the reference's `while ( !done )` body (txx:448-473)
+        double gd[3] = {0.0, 0.0, 0.0};
+        double value = 0.0, total = 0.0;
+        bool open = true;
+        // overlap = ((1 * wx) * wy) * wz in the reference's order; 1 * wx is wx, and the four wx * wy products are shared
+        // by the two z layers (same values, same association: bit-identical, 12 multiplications instead of 24)
+        const double wx[2] = {1.0 - dist[0], dist[0]}, wy[2] = {1.0 - dist[1], dist[1]}, wz[2] = {1.0 - dist[2], dist[2]};
+        const double wxy[4] = {wx[0] * wy[0], wx[1] * wy[0], wx[0] * wy[1], wx[1] * wy[1]};
+    #pragma unroll
+        for (int counter = 0; counter < 8; ++counter) {
+          if (open) {
+            const double overlap = wxy[counter & 3] * wz[counter >> 2];
+            if (overlap != 0.0) {
+              gd[0] += overlap * (double)ngrad[counter][0];
+              gd[1] += overlap * (double)ngrad[counter][1];
+              gd[2] += overlap * (double)ngrad[counter][2];
+              value += overlap * nval[counter];
+              total += overlap;
+            }
+            if (total == 1.0) open = false;
+          }
         }
-        if (total == 1.0) open = false;
-      }
-    }
-    // normal = (CovariantVector<float,3>) gradient; normal.Normalize()        txx:451-452
-    float normal[3] = {(float)gd[0], (float)gd[1], (float)gd[2]};
-    double sq = 0.0;
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-      const double c = (double)normal[k];
-      sq += c * c;
-    }
-    if (sq == 0.0) {   // norm == 0 (the square root of a positive double is positive)
-      done = true;  // zero gradient: the vertex stays where it is
-    } else {
-      done |= fabs(value - a.iso) < a.thr;  // txx:456  (the normalised normal is only used by the move below)
-      if (!done) {
-        // normal[k] = (float)((double)normal[k] / sqrt(sq)), txx:452: an IEEE square root and three IEEE divisions
-        // (~120 instructions).  Fast path: q = normal[k] * rsqrt(sq) is within a few ulp (double) of the exact
-        // quotient, so it rounds to the same float unless it lies within 64 ulp of a float rounding boundary (the low
-        // 29 mantissa bits near 2^28) or the float result would be subnormal; only then (2.4e-7 of the cases) the
-        // exact expressions run.  The result is bit-identical to the oracle's either way.
-        const double r = rsqrt(sq);
-        float fast[3];
-        bool risky = !(sq >= 1e-280 && sq <= 1e280);
-#pragma unroll
+        // normal = (CovariantVector<float,3>) gradient; normal.Normalize()        txx:451-452
+        float normal[3] = {(float)gd[0], (float)gd[1], (float)gd[2]};
+        double sq = 0.0;
+    #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const double q = (double)normal[k] * r;
-          fast[k] = (float)q;
-          // low 29 mantissa bits within 64 of the rounding boundary 2^28; |q| below the smallest normal float
-          // (biased exponent < 1023 - 126) unless it is an exact zero
-          const unsigned lo = (unsigned)__double2loint(q), hi = (unsigned)__double2hiint(q) & 0x7fffffffu;
-          risky |= ((lo & 0x1fffffffu) - (0x10000000u - 64u) < 128u) || (hi < 0x38100000u && (hi | lo) != 0u);
+          const double c = (double)normal[k];
+          sq += c * c;
         }
-        if (risky) {
-          const double norm = sqrt(sq);
-#pragma unroll
-          for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+        if (sq == 0.0) {   // norm == 0 (the square root of a positive double is positive)
+          done = true;  // zero gradient: the vertex stays where it is
         } else {
-          normal[0] = fast[0]; normal[1] = fast[1]; normal[2] = fast[2];
+          done |= fabs(value - a.iso) < a.thr;  // txx:456  (the normalised normal is only used by the move below)
+          if (!done) {
+            // normal[k] = (float)((double)normal[k] / sqrt(sq)), txx:452: an IEEE square root and three IEEE divisions
+            // (~120 instructions).  Fast path: q = normal[k] * rsqrt(sq) is within a few ulp (double) of the exact
+            // quotient, so it rounds to the same float unless it lies within 64 ulp of a float rounding boundary (the low
+            // 29 mantissa bits near 2^28) or the float result would be subnormal; only then (2.4e-7 of the cases) the
+            // exact expressions run.  The result is bit-identical to the oracle's either way.
+            const double r = rsqrt(sq);
+            float fast[3];
+            bool risky = !(sq >= 1e-280 && sq <= 1e280);
+    #pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const double q = (double)normal[k] * r;
+              fast[k] = (float)q;
+              // low 29 mantissa bits within 64 of the rounding boundary 2^28; |q| below the smallest normal float
+              // (biased exponent < 1023 - 126) unless it is an exact zero
+              const unsigned lo = (unsigned)__double2loint(q), hi = (unsigned)__double2hiint(q) & 0x7fffffffu;
+              risky |= ((lo & 0x1fffffffu) - (0x10000000u - 64u) < 128u) || (hi < 0x38100000u && (hi | lo) != 0u);
+            }
+            if (risky) {
+              const double norm = sqrt(sq);
+    #pragma unroll
+              for (int k = 0; k < 3; ++k) normal[k] = (float)((double)normal[k] / norm);
+            } else {
+              normal[0] = fast[0]; normal[1] = fast[1]; normal[2] = fast[2];
+            }
+            const double sign = (value < a.iso) ? +1.0 : -1.0;  // txx:463
+    #pragma unroll
+            for (int k = 0; k < 3; ++k) vert[k] = (float)((double)vert[k] + ((double)normal[k] * sign) * step);  // txx:466
+            step *= a.relax;                                  // txx:468
+            done |= numberOfSteps++ > a.max_steps;            // txx:469
+          }
         }
-        const double sign = (value < a.iso) ? +1.0 : -1.0;  // txx:463
-#pragma unroll
-        for (int k = 0; k < 3; ++k) vert[k] = (float)((double)vert[k] + ((double)normal[k] * sign) * step);  // txx:466
-        step *= a.relax;                                  // txx:468
-        done |= numberOfSteps++ > a.max_steps;            // txx:469
+        if (done) {
+          points[3 * i] = vert[0];
+          points[3 * i + 1] = vert[1];
+          points[3 * i + 2] = vert[2];
+          have = false;
+        } else {
+          locate();
+        }
       }
-    }
-    if (done) {
-      points[3 * i] = vert[0];
-      points[3 * i + 1] = vert[1];
-      points[3 * i + 2] = vert[2];
-      have = false;
-    }
+      n_active = __popc(__ballot_sync(0xffffffffu, have && base[0] == cell[0] && base[1] == cell[1] && base[2] == cell[2]));
+    } while (n_active >= a.refill);
   }
 }
 
