@@ -44,7 +44,7 @@ struct Knobs {
   int fuse_dbg = 0;          // CUB_FUSE_DBG: timing experiments (results are wrong): 1 = no sweep, 2 = no classification
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
   int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
-  int proj_ctas = 5;         // CUB_PROJ_CTAS_PER_SM
+  int proj_ctas = 6;         // CUB_PROJ_CTAS_PER_SM
   int proj_refill = 18;      // CUB_PROJ_REFILL: lanes of a warp that keep iterating before the warp serves the idle ones
 };
 
@@ -355,13 +355,10 @@ bool launch_fused_cfg(cub_handle h, const SweepArgs& ca, unsigned* ctr, unsigned
   fa.ctr = ctr; fa.done = done;
   fa.dbg = h->knobs.fuse_dbg;
   auto kern = k_classify_sweep<T, C, kFuseStages>;
-  static bool attr_set = false;  // (per instantiation; the attribute is per device function and idempotent)
-  if (!attr_set) {
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
-      cudaGetLastError();
-      return false;
-    }
-    attr_set = true;
+  // (set on every launch: the attribute belongs to the current device, and one process may drive several)
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
   }
   // persistent: every CTA resident (4 per SM: 64 registers x 256 threads, ~47 KB of shared memory)
   const unsigned long long want = std::max<unsigned long long>((fa.n_batches + 3) / 4, fa.n_tiles);
@@ -523,7 +520,7 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.fuse_dbg = env_int("CUB_FUSE_DBG", 0, 0, 3);
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
     h->knobs.scan_rows = env_int("CUB_SCAN_ROWS", 1, 0, 1);
-    h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 5, 1, 16);
+    h->knobs.proj_ctas = env_int("CUB_PROJ_CTAS_PER_SM", 6, 1, 16);
     h->knobs.proj_refill = env_int("CUB_PROJ_REFILL", 18, 1, 32);
   }
   bool ok = ensure(h, h->ctrl, kCtrlHead) == CUB_OK &&

@@ -107,7 +107,7 @@ __device__ __forceinline__ int clampi(long long v, int hi) { return v < 0 ? 0 : 
 // its vertex immediately takes the next one from a global counter instead of idling until the slowest vertex of
 // its warp is done.  The arithmetic per vertex is unchanged (and so are the results, bit for bit).
 template <typename T, bool ORIENTED>
-__global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
+__global__ void __launch_bounds__(128, ORIENTED ? 5 : 6) k_project(const ProjArgs a) {
   VolView<T> v{static_cast<const T*>(a.vol), a.g.X, a.g.Y, a.g.Zl, a.g.zg0, a.g.Zg};
   float gc[3];
   double inv_sp[3];
@@ -135,7 +135,11 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
   // voxel, so most iterations stay in the cell: the first version re-read 64 voxels per iteration).
   long long cell[3] = {LLONG_MIN, LLONG_MIN, LLONG_MIN};
   double nval[8];
-  float ngrad[8][3];
+  // the 24 gradient components live in shared memory, already widened to fp64 (exact), one column per thread: the
+  // interpolation then reads them with LDS.64 instead of converting them again on every pass (r2 profile: 24 of the
+  // ~50 conversions of a pass, on a conversion pipe that was 56 % busy), and 24 registers are free
+  __shared__ double s_ngrad[24][128];
+  double (*const ng)[128] = reinterpret_cast<double (*)[128]>(&s_ngrad[0][threadIdx.x]);  // ng[3 * node + axis][0]
   // continuous index of `vert`: base index (buffer-relative) and distances (shared by both interpolators)
   // (32-bit saturated base indices were measured in r2: same register count, 5.15 -> 5.33 ms)
   long long base[3] = {0, 0, 0};
@@ -239,10 +243,12 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           // non-finite centre pixel (0 * inf = NaN): for a finite one it adds +-0 to a sum that is never -0 (the
           // first addition to +0 cleared the sign), i.e. nothing.
           const bool odd = is_fp<T>::value && !(fabsf(mid) <= 3.402823466e38f);
-          { float s = 0.0f; s += (-gc[0]) * xm; if (odd) s += 0.0f * mid; s += gc[0] * xp; ngrad[counter][0] = s; }
-          { float s = 0.0f; s += (-gc[1]) * ym; if (odd) s += 0.0f * mid; s += gc[1] * yp; ngrad[counter][1] = s; }
-          { float s = 0.0f; s += (-gc[2]) * zm; if (odd) s += 0.0f * mid; s += gc[2] * zp; ngrad[counter][2] = s; }
-          if (ORIENTED) rotate_gradient(a.geom, ngrad[counter]);
+          float gt[3];
+          { float s = 0.0f; s += (-gc[0]) * xm; if (odd) s += 0.0f * mid; s += gc[0] * xp; gt[0] = s; }
+          { float s = 0.0f; s += (-gc[1]) * ym; if (odd) s += 0.0f * mid; s += gc[1] * yp; gt[1] = s; }
+          { float s = 0.0f; s += (-gc[2]) * zm; if (odd) s += 0.0f * mid; s += gc[2] * zp; gt[2] = s; }
+          if (ORIENTED) rotate_gradient(a.geom, gt);
+          ng[3 * counter + 0][0] = (double)gt[0]; ng[3 * counter + 1][0] = (double)gt[1]; ng[3 * counter + 2][0] = (double)gt[2];
         }
       } else {
 #pragma unroll 1
@@ -254,10 +260,11 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           gradient_at(v, gc, cx, cy, cz, gtmp);
           if (ORIENTED) rotate_gradient(a.geom, gtmp);
           const double nv = (double)v.at(cx, cy, cz);
+          ng[3 * counter + 0][0] = (double)gtmp[0]; ng[3 * counter + 1][0] = (double)gtmp[1]; ng[3 * counter + 2][0] = (double)gtmp[2];
           // (dynamic index into the register cache: written through a switch so that it stays in registers)
 #pragma unroll
           for (int q = 0; q < 8; ++q)
-            if (q == counter) { ngrad[q][0] = gtmp[0]; ngrad[q][1] = gtmp[1]; ngrad[q][2] = gtmp[2]; nval[q] = nv; }
+            if (q == counter) nval[q] = nv;
         }
       }
     }
@@ -277,9 +284,9 @@ __global__ void __launch_bounds__(128, 5) k_project(const ProjArgs a) {
           if (open) {
             const double overlap = wxy[counter & 3] * wz[counter >> 2];
             if (overlap != 0.0) {
-              gd[0] += overlap * (double)ngrad[counter][0];
-              gd[1] += overlap * (double)ngrad[counter][1];
-              gd[2] += overlap * (double)ngrad[counter][2];
+              gd[0] += overlap * ng[3 * counter + 0][0];
+              gd[1] += overlap * ng[3 * counter + 1][0];
+              gd[2] += overlap * ng[3 * counter + 2][0];
               value += overlap * nval[counter];
               total += overlap;
             }
