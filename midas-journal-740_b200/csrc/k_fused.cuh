@@ -71,6 +71,17 @@ __device__ __forceinline__ void bulk_load(void* dst, const void* src, unsigned b
                "l"(src), "r"(bytes), "r"(smem_addr(b))
                : "memory");
 }
+// the bitmask words are read again a few slices later by the consumers: ask L2 to keep them
+__device__ __forceinline__ unsigned long long l2_evict_last_policy() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_keep(uint32_t* p, const uint4 v, unsigned long long policy) {
+  asm volatile("st.global.L2::cache_hint.v4.b32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w),
+               "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, unsigned parity) {
   uint32_t ok;
   do {
@@ -111,6 +122,7 @@ __device__ __forceinline__ void fused_producer(const FuseArgs& a, const T iso, F
 
   // the batch being issued: tasks [icur, iend), icur = group igrp of row irow (kept incrementally: no division per task)
   unsigned icur = 0, iend = 0, irow = 0, igrp = 0;
+  const unsigned long long keep = l2_evict_last_policy();
   // the ticket of the NEXT batch is requested while the current one is being issued (lane 0 holds it; an atomic's
   // round trip is worth several tasks)
   unsigned next_b = 0;
@@ -183,7 +195,7 @@ __device__ __forceinline__ void fused_producer(const FuseArgs& a, const T iso, F
         uint32_t w[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) w[k] = __ballot_sync(0xffffffffu, !(sp[(k4 + k) * 32] < iso));
-        if (lane == 0) *reinterpret_cast<uint4*>(dst + k4) = make_uint4(w[0], w[1], w[2], w[3]);
+        if (lane == 0) st_keep(dst + k4, make_uint4(w[0], w[1], w[2], w[3]), keep);
       }
     } else {
       // ragged end of a row: lanes past it re-read the row's last voxel ("replicate bit X-1", k_classify.cuh)
