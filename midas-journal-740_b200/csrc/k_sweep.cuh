@@ -287,8 +287,6 @@ __device__ __forceinline__ void sweep_tile(const SweepArgs& a, SweepSmem<C>& sm,
             packed = nv | (nf << 10);
             // (r2 also tried two 16-byte half records, each written only where it has a bit: fewer bytes stored, but a
             //  16-byte store leaves half a 32-byte L2 sector to be filled from DRAM - the fused kernel went 0.88 -> 0.98 ms)
-            // (r2 also tried two 16-byte half records, each written only where it has a bit: fewer bytes stored, but a
-            //  16-byte store leaves half a 32-byte L2 sector to be filled from DRAM - the fused kernel went 0.88 -> 0.98 ms)
             if (nv && a.own) {  // k_assign walks these instead of sweeping again
               uint4* __restrict__ o = a.own + 2 * ((size_t)z * plane_entries + (size_t)(e0 + k * a.EW));
               __stcs(o, make_uint4(O[0], O[1], O[2], O[3]));
