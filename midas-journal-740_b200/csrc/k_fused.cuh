@@ -29,7 +29,6 @@ namespace cbr {
 constexpr int kFuseStageBytes = 4096;   // one task: 32 words of 4-byte pixels, 16 words of 8-byte pixels
 constexpr int kFuseProducerWarps = 4;
 constexpr int kFuseThreads = 256;
-constexpr int kFuseBatch = 16;          // tasks per ticket / per publication (one release + atomic per 64 KB)
 constexpr int kFuseProducerRegs = 32, kFuseConsumerRegs = 96;   // 128 * (32 + 96) = 256 * 64
 
 struct FuseArgs {
@@ -37,6 +36,7 @@ struct FuseArgs {
   const void* vol;
   uint32_t* bits;
   unsigned n_tasks, groups_per_row, tasks_per_slice, n_batches;
+  unsigned batch;             // tasks per ticket and per publication (8: one release + atomic per 32 KB)
   unsigned n_tiles, gx, gy;   // sweep tiles; ticket -> (bx, by, bz), bz slowest
   unsigned* ctr;              // [0] producer ticket, [1] consumer ticket (zeroed before the launch)
   unsigned* done;             // [Zl] classification tasks completed per slice (zeroed before the launch)
@@ -140,8 +140,8 @@ __device__ __forceinline__ void fused_producer(const FuseArgs& a, const T iso, F
         return false;
       }
       if (lane == 0) next_b = atomicAdd(a.ctr, 1u);
-      icur = b * kFuseBatch;
-      iend = min(icur + (unsigned)kFuseBatch, a.n_tasks);
+      icur = b * a.batch;
+      iend = min(icur + a.batch, a.n_tasks);
       irow = icur / a.groups_per_row;
       igrp = icur - irow * a.groups_per_row;
     }
@@ -208,7 +208,7 @@ __device__ __forceinline__ void fused_producer(const FuseArgs& a, const T iso, F
     __syncwarp();  // every lane has read the stage before it is filled again
     if (sig_n && task != sig_first + sig_n) publish();
     if (!sig_n) sig_first = task;
-    if (++sig_n == (unsigned)kFuseBatch) publish();
+    if (++sig_n == a.batch) publish();
     if (!issue(head)) --inflight;
     head = (head + 1 == S) ? 0 : head + 1;
   }
