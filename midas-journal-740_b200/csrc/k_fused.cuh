@@ -3,23 +3,28 @@
 //
 // Reference: the suitability / neighbour predicate (txx:139-141, 167; k_classify.cuh) and the vertex lookup of the hot
 // loop (txx:179-194; k_sweep.cuh).  Nothing changes in what is computed: the bitmask, the packed counts, the active
-// masks and the ownership records are the ones the two separate kernels write.
+// masks and the ownership records are the ones the two separate kernels write (tests/test_gpu_fused.py compares them).
 //
 // Why: run one after the other, K1 keeps the memory system at the copy peak with a quarter of the issue slots, then K2a
-// fills two thirds of the issue slots while HBM idles.  Here every CTA holds both roles:
-//   * warpgroup 0 = four PRODUCER warps.  Each owns a private ring of kFuseStages 2 KB shared-memory stages that one
+// fills two thirds of the issue slots while HBM idles (0.66 + 0.39 ms for 1024^3 float32).  Here every CTA holds both
+// roles (0.83 ms, bound by the DRAM traffic of the two together):
+//   * warpgroup 0 = four PRODUCER warps.  Each owns a private ring of kFuseStages 4 KB shared-memory stages that one
 //     elected lane fills with TMA bulk copies (cp.async.bulk global -> shared, completion on an mbarrier), so the
 //     bytes in flight per SM are set by shared memory, not by registers or by the number of resident warps; the warp
-//     reads a landed stage one voxel per lane, the ballot of `!(v < iso)` is the output word (as in k_classify).
-//     Tasks (<= 2 KB of one row) are handed out in raster order, in batches of kFuseBatch through one atomic ticket;
-//     a finished batch is published with a fence + one atomic add per slice into done[z].
+//     reads a landed stage one voxel per lane, the ballot of `!(v < iso)` is the output word (as in k_classify), and
+//     lane 0 stores the words with an L2 evict-last hint (the consumers read them a few slices later).
+//     Tasks (<= 4 KB of one row) are handed out in raster order, `batch` at a time through one atomic ticket (the next
+//     ticket is requested while the current batch is issued); a finished batch is published with one release-add per
+//     slice it touches into done[z].
 //   * warpgroup 1 = four CONSUMER warps = one sweep tile at a time (sweep_tile of k_sweep.cuh on named barrier 1),
-//     tiles taken in z-major order through a second ticket; before a tile starts, its warps wait until every slice it
-//     reads is complete (done[z] == tasks per slice).
-//   * setmaxnreg moves registers from the producers (32) to the consumers (96): four CTAs = four sweep tiles per SM,
-//     as many as the stand-alone sweep kernel has.
+//     tiles taken in z-major order through a second ticket; before a tile starts, one of its warps waits (acquire
+//     loads, growing back-off) until every slice the tile reads is complete (done[z] == tasks per slice).
+//   * setmaxnreg moves registers from the producers (32) to the consumers (96): four CTAs = four sweep tiles per SM.
 // Producers never wait for anything but their own copies and every CTA has producers, so the kernel cannot deadlock,
 // whatever part of the grid is resident.
+// What bounds it (r2, ncu): 4.50 GB read + 0.85 GB written in 0.87 ms = 94 % of the measured copy peak before the
+// evict-last hint and the smaller batches; how far the consumers run behind the producers (what all producer warps
+// have in flight: 2368 warps x batch x 4 KB) decides whether the bitmask words are still in L2 when they are read.
 #pragma once
 #include "k_classify.cuh"
 #include "k_sweep.cuh"
