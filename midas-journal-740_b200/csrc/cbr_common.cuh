@@ -43,6 +43,16 @@ __host__ __device__ constexpr int corner_oz(int l) { return (l >= 4) ? 1 : 0; }
 __device__ __constant__ const int8_t kFaceCorners[6][4] = {{0, 4, 7, 3}, {0, 1, 5, 4}, {1, 2, 6, 5},
                                                            {2, 3, 7, 6}, {0, 3, 2, 1}, {4, 5, 6, 7}};
 
+// Programmatic dependent launch (the kernels of a step are queued with cudaLaunchAttributeProgrammaticStreamSerialization):
+// the first statement of every kernel of the hot path.  `wait` returns once the kernel launched before this one in the
+// stream has completed and its writes are visible (a no-op for a plain launch); `launch_dependents` then lets the next
+// kernel's CTAs be scheduled as this grid drains, up to their own `wait` - launch latency and prologue leave the
+// critical path (a step of a thin z-slab is eight kernels of 5..150 us each).
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct Geom {
   double spacing[3];
   double origin[3];

@@ -42,6 +42,7 @@ struct Knobs {
   int fuse_tz = 0;           // CUB_FUSE_TZ: slices per sweep tile of the fused kernel (0: pick_tz)
   int fuse_ctas = 4;         // CUB_FUSE_CTAS_PER_SM
   int fuse_batch = 8;        // CUB_FUSE_BATCH: classification tasks (4 KB of a row each) per ticket and per publication
+  int pdl = -1;              // CUB_PDL: programmatic dependent launch between the kernels of a step (-1: by volume size)
   int fuse_dbg = 0;          // CUB_FUSE_DBG: timing experiments (results are wrong): 1 = no sweep, 2 = no classification
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
   int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
@@ -127,6 +128,7 @@ struct cub_handle_s {
   unsigned* d_fuse_done = nullptr;
   unsigned* d_fuse_ctr = nullptr;
   bool fused_last = false;     // the last count ran K1 + K2a as the fused kernel
+  bool pdl_on = false;         // the kernels of the current run are queued with programmatic dependent launch
   unsigned long long* d_status = nullptr;
   DevBuf<uint32_t> vtx;      // K3a -> K3b: the lattice corner of every vertex id
   DevBuf<uint32_t> vsl;      // k_slice_index: per-slice first ids, then the slice of each k_vertices block
@@ -263,6 +265,24 @@ struct Timer {
     }
   }
 };
+
+// One kernel of a step on the handle's stream.  With programmatic dependent launch the kernel may be scheduled while
+// its predecessor in the stream drains; every kernel launched through here starts with pdl_enter() (cbr_common.cuh).
+template <typename... P, typename... A>
+cudaError_t launch_step(cub_handle h, void (*kern)(P...), dim3 grid, dim3 block, bool pdl, A&&... args) {
+  h->launches++;
+  if (!h->pdl_on || !pdl) {
+    kern<<<grid, block, 0, h->stream>>>(std::forward<A>(args)...);
+    return cudaGetLastError();
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = h->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
 
 // K1 on the local slices [z0, z1) (rows are independent), on `stream`, with at most ctas_per_sm resident CTAs
 template <typename T> struct is_packable { static constexpr bool value = false; };
@@ -523,6 +543,7 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.fuse_tz = env_int("CUB_FUSE_TZ", 0, 0, 32);
     h->knobs.fuse_ctas = env_int("CUB_FUSE_CTAS_PER_SM", 4, 1, 4);
     h->knobs.fuse_dbg = env_int("CUB_FUSE_DBG", 0, 0, 3);
+    h->knobs.pdl = env_int("CUB_PDL", -1, -1, 1);
     h->knobs.fuse_batch = env_int("CUB_FUSE_BATCH", 8, 1, 256);
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);
     h->knobs.scan_rows = env_int("CUB_SCAN_ROWS", 1, 0, 1);
@@ -788,6 +809,9 @@ int count_launch(cub_handle h, const cub_params* p) {
   ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = h->raster ? nullptr : h->own.p;
   ca.slice_any = h->d_slice_any;
   {
+    // Programmatic dependent launch pays where the kernels are short (measured r2, gyroid f32: a 132-slice slab of
+    // 1024^2 rows 0.330 -> 0.319 ms per step, the whole 1024^3 volume 1.985 -> 2.02 ms): on below 300 M voxels.
+    h->pdl_on = h->knobs.pdl < 0 ? (unsigned long long)g.X * g.Y * g.Zl < 300000000ull : h->knobs.pdl != 0;
     // K1 + K2a: one warp-specialised kernel where it applies (k_fused.cuh), else K1 then K2a on the handle's stream.
     // The control block (tickets, per-slice progress, scan descriptors, slice occupancy) is cleared first.
     CU_TRY(h, cudaMemsetAsync(h->ctrl.p, 0, h->ctrl_used * sizeof(unsigned long long), h->stream));
@@ -823,14 +847,11 @@ int count_launch(cub_handle h, const cub_params* p) {
     sa.mark_row_c = (h->own_z0 > 0) ? (unsigned)((size_t)(h->zs0 + 1) * h->EY) : 0xffffffffu;
     sa.rows_per_tile = (unsigned)rows_per_tile; sa.n_tiles = (unsigned)n_tiles;
     sa.status = h->d_status; sa.ticket = h->d_ticket; sa.info = h->d_info;
-    if (scan_rows && h->NS == 1) k_seg_scan_rows<1><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
-    else if (scan_rows) k_seg_scan_rows<2><<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
-    else k_seg_scan<<<(unsigned)n_tiles, kScanThreads, 0, h->stream>>>(sa);
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
-    k_finalize_info<<<1, 256, 0, h->stream>>>(h->d_info, h->raster ? 1 : 0, h->d_slice_any, h->owner_z_min, h->zs1);
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
+    if (scan_rows && h->NS == 1) CU_TRY(h, launch_step(h, k_seg_scan_rows<1>, dim3((unsigned)n_tiles), dim3(kScanThreads), true, sa));
+    else if (scan_rows) CU_TRY(h, launch_step(h, k_seg_scan_rows<2>, dim3((unsigned)n_tiles), dim3(kScanThreads), true, sa));
+    else CU_TRY(h, launch_step(h, k_seg_scan, dim3((unsigned)n_tiles), dim3(kScanThreads), true, sa));
+    CU_TRY(h, launch_step(h, k_finalize_info, dim3(1), dim3(256), true, h->d_info, h->raster ? 1 : 0, (const uint32_t*)h->d_slice_any,
+                          h->owner_z_min, h->zs1));
     if (h->timing) {
       cudaEventRecord(h->ev[1], h->stream);
       cudaEventSynchronize(h->ev[1]);
@@ -916,9 +937,7 @@ int emit_vertex_stage(cub_handle h, bool exact) {
   if (!exact && !h->caps_checked) {
     // the one comparison of the device-side counts with the capacity of the buffers (the quads are checked again,
     // with the cell buffers of the emission, in emit_launch)
-    k_check_caps<<<1, 32, 0, h->stream>>>(h->d_info, make_caps(h, ~0ull));
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, launch_step(h, k_check_caps, dim3(1), dim3(32), true, h->d_info, make_caps(h, ~0ull)));
   }
   // the points of the vertices the slab underneath owns are only needed by the projected triangle split
   const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
@@ -937,10 +956,8 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       a.vtx = h->vtx.p; a.info = h->d_info; a.caps = make_caps(h, ~0ull);
       const int rows = kAssignThreads / 32;
       const dim3 grid((g.Wx + 31) / 32, (h->EY + rows - 1) / rows, nz + 1);
-      if (exact) k_assign<false><<<grid, kAssignThreads, 0, h->stream>>>(a);
-      else k_assign<true><<<grid, kAssignThreads, 0, h->stream>>>(a);
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
+      if (exact) CU_TRY(h, launch_step(h, k_assign<false>, grid, dim3(kAssignThreads), true, a));
+      else CU_TRY(h, launch_step(h, k_assign<true>, grid, dim3(kAssignThreads), true, a));
     }
     if (n_blocks > 0) {
       // K3b: points + corner -> id map
@@ -948,8 +965,7 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       si.seg = h->seg.p; si.plane_segs = (size_t)h->EY * h->NS; si.z_first = h->owner_z_min; si.nz = nz;
       si.slice_first = h->vsl.p; si.block_slice = h->vsl.p + nz + 1; si.n_blocks = n_blocks; si.ids_per_block = kVertexBlockIds;
       const unsigned si_threads = n_blocks > (unsigned)nz + 1 ? n_blocks : (unsigned)nz + 1;
-      k_slice_index<<<(si_threads + 255) / 256, 256, 0, h->stream>>>(si);
-      h->launches++;
+      CU_TRY(h, launch_step(h, k_slice_index, dim3((si_threads + 255) / 256), dim3(256), true, si));
       VertexArgs a{};
       a.vtx = h->vtx.p; a.caps = make_caps(h, ~0ull); a.write_ghost_points = ghost_points ? 1 : 0;
       a.info = h->d_info;
@@ -960,12 +976,10 @@ int emit_vertex_stage(cub_handle h, bool exact) {
       a.coff[0] = (int)(h->i0[0] - h->pad); a.coff[1] = (int)(h->i0[1] - h->pad); a.coff[2] = (int)(h->i0[2] + g.zg0 - h->pad);
       a.points = h->points.p; a.perm = h->perm.p;
       if (!exact) {
-        if (h->geom.oriented) k_vertices<true, true><<<n_blocks, 256, 0, h->stream>>>(a);
-        else k_vertices<false, true><<<n_blocks, 256, 0, h->stream>>>(a);
-      } else if (h->geom.oriented) k_vertices<true, false><<<n_blocks, 256, 0, h->stream>>>(a);
-      else k_vertices<false, false><<<n_blocks, 256, 0, h->stream>>>(a);
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
+        if (h->geom.oriented) CU_TRY(h, launch_step(h, k_vertices<true, true>, dim3(n_blocks), dim3(256), true, a));
+        else CU_TRY(h, launch_step(h, k_vertices<false, true>, dim3(n_blocks), dim3(256), true, a));
+      } else if (h->geom.oriented) CU_TRY(h, launch_step(h, k_vertices<true, false>, dim3(n_blocks), dim3(256), true, a));
+      else CU_TRY(h, launch_step(h, k_vertices<false, false>, dim3(n_blocks), dim3(256), true, a));
     }
   } else {
     // raster order: vertex id = corner slot, points straight from the active masks
@@ -1015,9 +1029,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
   if (h->timing) cudaEventRecord(h->ev[4], h->stream);
   if (!exact) {
     // one comparison of the device-side counts with the capacity of the buffers, for every kernel of the emission
-    k_check_caps<<<1, 32, 0, h->stream>>>(h->d_info, make_caps(h, quads_cap));
-    h->launches++;
-    CU_TRY(h, cudaGetLastError());
+    CU_TRY(h, launch_step(h, k_check_caps, dim3(1), dim3(32), true, h->d_info, make_caps(h, quads_cap)));
     h->caps_checked = true;
   }
   const bool ghost_points = (mode == kEmitScratchQuads) && h->owner_z_min < h->zs0;
@@ -1045,13 +1057,16 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       a.celldata = cd ? h->celldata.p : nullptr;
       a.pix_bytes = h->pix_bytes;
       const dim3 blocks((g.Wx + 31) / 32, (g.Y + kFaceThreads / 32 - 1) / (kFaceThreads / 32), h->zs1 - h->zs0);
-#define CUB_FACES(IdT, MODE)                                                                   \
-      do {                                                                                       \
-        if (!exact) {                                                                            \
-          if (cd) k_faces<IdT, MODE, true, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);     \
-          else k_faces<IdT, MODE, false, true><<<blocks, kFaceThreads, 0, h->stream>>>(a);       \
-        } else if (cd) k_faces<IdT, MODE, true, false><<<blocks, kFaceThreads, 0, h->stream>>>(a); \
-        else k_faces<IdT, MODE, false, false><<<blocks, kFaceThreads, 0, h->stream>>>(a);        \
+      // (behind an event of another stream the launch is an ordinary one: the id base comes from the count exchange)
+      const bool pdl = h->wait_before_faces == nullptr;
+      cudaError_t fe = cudaSuccess;
+#define CUB_FACES(IdT, MODE)                                                                                  \
+      do {                                                                                                      \
+        if (!exact) {                                                                                           \
+          if (cd) fe = launch_step(h, k_faces<IdT, MODE, true, true>, blocks, dim3(kFaceThreads), pdl, a);      \
+          else fe = launch_step(h, k_faces<IdT, MODE, false, true>, blocks, dim3(kFaceThreads), pdl, a);        \
+        } else if (cd) fe = launch_step(h, k_faces<IdT, MODE, true, false>, blocks, dim3(kFaceThreads), pdl, a); \
+        else fe = launch_step(h, k_faces<IdT, MODE, false, false>, blocks, dim3(kFaceThreads), pdl, a);         \
       } while (0)
       if (mode == kEmitScratchQuads) CUB_FACES(uint32_t, kEmitScratchQuads);
       else if (mode == kEmitQuads && id_bytes == 4) CUB_FACES(uint32_t, kEmitQuads);
@@ -1059,8 +1074,7 @@ int emit_launch(cub_handle h, int id_bytes, bool exact) {
       else if (id_bytes == 4) CUB_FACES(uint32_t, kEmitTrisFixed);
       else CUB_FACES(unsigned long long, kEmitTrisFixed);
 #undef CUB_FACES
-      h->launches++;
-      CU_TRY(h, cudaGetLastError());
+      CU_TRY(h, fe);
     }
     t.stop();
   }

@@ -118,6 +118,7 @@ struct FaceSmem {
 // lanes whose words have none.
 template <typename IdT, int MODE, bool CD, bool GUARD>
 __global__ void __launch_bounds__(kFaceThreads, 12) k_faces(const FaceArgs a) {
+  pdl_enter();
   __shared__ FaceSmem sm;
   // GUARD: the host queued the launch without knowing the counts (cub_emit_async): one check of the device-side
   // counts against the capacity of the buffers, for the whole kernel.  The counts are requested here and looked at

@@ -255,6 +255,7 @@ __device__ __forceinline__ void fused_consumer(const FuseArgs& a, SweepSmem<C>& 
 
 template <typename T, typename C, int S>
 __global__ void __launch_bounds__(kFuseThreads, 4) k_classify_sweep(const FuseArgs a, const T iso) {
+  pdl_enter();
   static_assert(C::NTP == 128, "the consumer role is one warpgroup");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FuseSmem<C, S>& sm = *reinterpret_cast<FuseSmem<C, S>*>(smem_raw);

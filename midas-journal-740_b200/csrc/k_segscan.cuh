@@ -64,6 +64,7 @@ struct Caps {
 };
 // one thread, queued in front of an emission whose host does not know the counts: the verdict every GUARD kernel reads
 __global__ void k_check_caps(unsigned long long* info, Caps c) {
+  pdl_enter();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const unsigned long long tv = info[kInfoTotV], tc = info[kInfoTotC], q = info[kInfoTotF] - info[kInfoMarkF];
   const bool fits = (c.raster ? tc : tv) <= c.points && (c.raster || tc <= c.perm) && q <= c.quads;
@@ -123,6 +124,7 @@ __device__ __forceinline__ unsigned long long lookback(const unsigned long long*
 }
 
 __global__ void __launch_bounds__(kScanThreads) k_seg_scan(const SegScanArgs a) {
+  pdl_enter();
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_part[3][kScanWarps];
   __shared__ unsigned long long s_excl[3];
@@ -248,6 +250,7 @@ constexpr int kScanBatches = 4;
 
 template <int NS>
 __global__ void __launch_bounds__(kScanThreads) k_seg_scan_rows(const SegScanArgs a) {
+  pdl_enter();
   __shared__ unsigned int s_tile;
   __shared__ unsigned long long s_part[3][kScanWarps];
   __shared__ unsigned long long s_excl[3];
@@ -345,6 +348,7 @@ __global__ void __launch_bounds__(kScanThreads) k_seg_scan_rows(const SegScanArg
 // this library implements the intended rule and reports the case through cub_last_warning.
 __global__ void __launch_bounds__(256) k_finalize_info(unsigned long long* info, int raster, const uint32_t* slice_any,
                                                        int z_begin, int z_end) {
+  pdl_enter();
   __shared__ int s_first, s_last, s_hole;
   if (threadIdx.x == 0) { s_first = INT_MAX; s_last = -1; s_hole = 0; }
   __syncthreads();

@@ -50,6 +50,7 @@ constexpr int kAssignThreads = 128;  // (one row segment per warp)
 // z = planes of the scan range (one more than its voxel slices: the top corner plane)
 template <bool GUARD>
 __global__ void __launch_bounds__(kAssignThreads) k_assign(const AssignArgs a) {
+  pdl_enter();
   const bool fits = !GUARD || emission_fits(a.info);  // (looked at after the scan: see k_faces)
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * 32 + lane, y = blockIdx.y * (kAssignThreads / 32) + (threadIdx.x >> 5), z = a.z_begin + blockIdx.z;
@@ -136,6 +137,7 @@ struct SliceIndexArgs {
 };
 
 __global__ void __launch_bounds__(256) k_slice_index(const SliceIndexArgs a) {
+  pdl_enter();
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t <= (uint32_t)a.nz) a.slice_first[t] = t < (uint32_t)a.nz ? __ldg(&a.seg[(size_t)(a.z_first + t) * a.plane_segs].x) : 0xffffffffu;
   if (t >= a.n_blocks) return;
@@ -155,6 +157,7 @@ constexpr int kVertexBlockIds = 256 * kVertexPerThread;   // (the kernel is a ch
 // is checked against the capacity of its buffer)
 template <bool ORIENTED, bool GUARD>
 __global__ void __launch_bounds__(256, ORIENTED ? 4 : 8) k_vertices(const VertexArgs a) {
+  pdl_enter();
   // GUARD: the number of vertices comes from the device-side run info (the grid is sized for the buffers' capacity)
   const size_t id0 = (size_t)blockIdx.x * kVertexBlockIds + threadIdx.x;
   uint32_t v[kVertexPerThread];
