@@ -43,7 +43,6 @@ struct Knobs {
   int fuse_ctas = 4;         // CUB_FUSE_CTAS_PER_SM
   int fuse_batch = 8;        // CUB_FUSE_BATCH: classification tasks (4 KB of a row each) per ticket and per publication
   int pdl = -1;              // CUB_PDL: programmatic dependent launch between the kernels of a step (-1: by volume size)
-  int fuse_dbg = 0;          // CUB_FUSE_DBG: timing experiments (results are wrong): 1 = no sweep, 2 = no classification
   int scan_ctas = 8;         // CUB_SCAN_CTAS_PER_SM
   int scan_rows = 1;         // CUB_SCAN_ROWS: the one-pass scan kernel for rows of at most two segments
   int proj_ctas = 6;         // CUB_PROJ_CTAS_PER_SM
@@ -378,7 +377,6 @@ bool launch_fused_cfg(cub_handle h, const SweepArgs& ca, unsigned* ctr, unsigned
   if (tiles >= (1ull << 31)) return false;
   fa.n_tiles = (unsigned)tiles; fa.gx = (unsigned)gx; fa.gy = (unsigned)gy;
   fa.ctr = ctr; fa.done = done;
-  fa.dbg = h->knobs.fuse_dbg;
   auto kern = k_classify_sweep<T, C, kFuseStages>;
   // (set on every launch: the attribute belongs to the current device, and one process may drive several)
   if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(Smem)) != cudaSuccess) {
@@ -542,7 +540,6 @@ int cub_create(int device, void* stream, cub_handle* out) {
     h->knobs.fuse = env_int("CUB_FUSE", 1, 0, 1);
     h->knobs.fuse_tz = env_int("CUB_FUSE_TZ", 0, 0, 32);
     h->knobs.fuse_ctas = env_int("CUB_FUSE_CTAS_PER_SM", 4, 1, 4);
-    h->knobs.fuse_dbg = env_int("CUB_FUSE_DBG", 0, 0, 3);
     h->knobs.pdl = env_int("CUB_PDL", -1, -1, 1);
     h->knobs.fuse_batch = env_int("CUB_FUSE_BATCH", 8, 1, 256);
     h->knobs.scan_ctas = env_int("CUB_SCAN_CTAS_PER_SM", 8, 1, 32);

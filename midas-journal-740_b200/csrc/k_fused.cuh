@@ -45,7 +45,6 @@ struct FuseArgs {
   unsigned n_tiles, gx, gy;   // sweep tiles; ticket -> (bx, by, bz), bz slowest
   unsigned* ctr;              // [0] producer ticket, [1] consumer ticket (zeroed before the launch)
   unsigned* done;             // [Zl] classification tasks completed per slice (zeroed before the launch)
-  int dbg;                    // CUB_FUSE_DBG (timing experiments only): 1 = no sweep, 2 = no classification, no waiting
 };
 
 template <int S>
@@ -116,7 +115,6 @@ __device__ __forceinline__ void fused_producer(const FuseArgs& a, const T iso, F
   const Grid& g = a.sw.g;
   unsigned long long* full = sm.full[warp];
   uint4* meta = sm.meta[warp];   // per stage: {row, first word, task, voxels}
-  if (a.dbg & 2) return;
   if (lane == 0) {
 #pragma unroll
     for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
@@ -239,7 +237,7 @@ __device__ __forceinline__ void fused_consumer(const FuseArgs& a, SweepSmem<C>& 
     // One warp polls, with a growing back-off (every consumer of the GPU watches the same few counters: a tight
     // loop in all of them would queue up in front of the one L2 slice that also serves the producers' publications):
     // first the top slice alone - batches finish roughly in raster order - then all of them.
-    if (t < 32 && !(a.dbg & 2)) {
+    if (t < 32) {
       unsigned ns = 256;
       while (ld_acquire(a.done + need_hi) < a.tasks_per_slice) {
         __nanosleep(ns);
@@ -249,7 +247,7 @@ __device__ __forceinline__ void fused_consumer(const FuseArgs& a, SweepSmem<C>& 
         while (ld_acquire(a.done + z) < a.tasks_per_slice) __nanosleep(1024);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(C::NTP) : "memory");  // (orders the other warps' loads after the acquires)
-    if (!(a.dbg & 1)) sweep_tile<C, true>(a.sw, sm, t, (int)bx, (int)by, (int)bz);
+    sweep_tile<C, true>(a.sw, sm, t, (int)bx, (int)by, (int)bz);
   }
 }
 
