@@ -372,6 +372,9 @@ def main():
                 "achieved": k1_gbs, "peak": peak, "unit": "GB/s",
                 "frac": k1_gbs / peak, "traffic": traffic if N == 1 and S == 1024 else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_k1, "avg_launch_ms": kavg["classify"],
+                # the same launch against the bytes it actually moves (ncu dram__bytes of one launch, profiles/traffic.json):
+                # the fused kernel also writes the sweep's intermediates, which the algorithmic figure does not count
+                "traffic_frac": (traffic / (kavg["classify"] * 1e-3) / 1e9 / peak) if (traffic and N == 1 and S == 1024 and kavg["classify"] > 0) else None,
                 "kernel_ms": kavg,
                 "classify_plus_compact": {"ms": cc_ms, "achieved": alg_k1 / (cc_ms * 1e-3) / 1e9,
                                           "frac_input_only": alg_k1 / (cc_ms * 1e-3) / 1e9 / peak,
