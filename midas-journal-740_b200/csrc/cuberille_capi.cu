@@ -806,10 +806,10 @@ int count_launch(cub_handle h, const cub_params* p) {
   ca.cnt = h->cnt.p; ca.act = h->act.p; ca.own = h->raster ? nullptr : h->own.p;
   ca.slice_any = h->d_slice_any;
   {
-    // Programmatic dependent launch pays where the kernels are short (measured r2, gyroid f32: a 132-slice slab of
-    // 1024^2 rows 0.330 -> 0.319 ms per step, a 516-slice slab 1.078 -> 1.070, the whole 1024^3 volume 1.985 -> 2.02 ms):
-    // on below 600 M voxels.
-    h->pdl_on = h->knobs.pdl < 0 ? (unsigned long long)g.X * g.Y * g.Zl < 600000000ull : h->knobs.pdl != 0;
+    // Programmatic dependent launch pays where the kernels are short.  Measured r2, gyroid f32, same box, off -> on:
+    // 512^3 0.456 -> 0.444 ms per step, a 132-slice slab of 1024^2 rows 0.330 -> 0.319, Marschner-Lobb 512^3 0.405 -> 0.395;
+    // 768^3 (453 M voxels) 1.112 -> 1.115, 1024^3 1.985 -> 2.02.  On below 300 M voxels per handle.
+    h->pdl_on = h->knobs.pdl < 0 ? (unsigned long long)g.X * g.Y * g.Zl < 300000000ull : h->knobs.pdl != 0;
     // K1 + K2a: one warp-specialised kernel where it applies (k_fused.cuh), else K1 then K2a on the handle's stream.
     // The control block (tickets, per-slice progress, scan descriptors, slice occupancy) is cleared first.
     CU_TRY(h, cudaMemsetAsync(h->ctrl.p, 0, h->ctrl_used * sizeof(unsigned long long), h->stream));
