@@ -20,6 +20,26 @@ def test_reference_known_answers(row):
         assert np.isfinite(m.points).all()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_literal_lookup_equals_closed_form_on_noise(seed):
+    """the same on iid noise (every corner configuration, inside voxels on the image border, ragged shapes): the
+    verbatim loop with its two lookup planes and the closed form number every vertex and cell alike, as long as no
+    slice between two occupied ones is empty (the reference's lookup-plane rotation only advances on inside voxels)"""
+    O = oracle()
+    rng = np.random.default_rng(1000 + seed)
+    shape = tuple(int(v) for v in rng.integers(1, 14, size=2)) + (int(rng.integers(1, 70)),)
+    fill = rng.uniform(0.15, 0.85)
+    vol = (rng.random(shape) < fill).astype(np.uint8) * 200
+    for z in range(shape[0]):  # one inside voxel per slice
+        vol[z, rng.integers(0, shape[1]), rng.integers(0, shape[2])] = 200
+    for tri in (False, True):
+        a = O.cuberille(vol, 100, triangles=tri, project=False, mode=O.LITERAL)
+        b = O.cuberille(vol, 100, triangles=tri, project=False, mode=O.CLOSED_FORM)
+        assert a.points.shape == b.points.shape and a.cells.shape == b.cells.shape, (shape, fill)
+        assert np.array_equal(a.cells, b.cells), (shape, fill)
+        assert np.array_equal(a.points.view(np.uint32), b.points.view(np.uint32)), (shape, fill)
+
+
 @pytest.mark.parametrize("fixture,iso", [("fuel", 15), ("nucleon", 140), ("blob3", 200)])
 def test_literal_lookup_equals_closed_form(fixture, iso):
     """the two-plane std::map emulation (txx:155-161,186-191) and the first-touch closed form give
